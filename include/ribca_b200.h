@@ -1,0 +1,236 @@
+/*
+ * ribca_b200.h - C ABI of libribca_b200.so: RIBCA's per-cell annotation hot path on B200 (sm_100a).
+ *
+ * The reference (sun-huangqingbo/multiplexed-image-annotator) is pure Python and has no FFI of its
+ * own; its drop-in boundary is the Python API.  This library sits UNDER the
+ * Python classes that mirror that API and replaces, one entry point per stage, the reference
+ * functions cited beside each declaration (paths relative to the reference root,
+ * cta/ = src/multiplexed_image_annotator/cell_type_annotation/).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative RIBCA_E* code; ribca_last_error() returns
+ *     a thread-local message for the last failure.  No C++ exception crosses the boundary.
+ *   - all buffers are caller-allocated; pointers are DEVICE pointers unless the parameter name
+ *     starts with h_ (small host arrays that are copied into kernel parameters).
+ *   - no hidden allocation: scratch is an explicit `workspace` sized by the matching
+ *     *_workspace_bytes() query.  Calls are asynchronous on `stream` (a cudaStream_t) and
+ *     re-entrant per stream.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     RIBCA_ECUDA.
+ */
+#ifndef RIBCA_B200_H
+#define RIBCA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIBCA_OK 0
+#define RIBCA_EINVAL (-1)   /* bad argument                           */
+#define RIBCA_ECUDA (-2)    /* CUDA runtime / driver error            */
+#define RIBCA_EWORKSPACE (-3) /* workspace too small                  */
+#define RIBCA_EUNSUPPORTED (-4)
+
+#define RIBCA_PATCH 40         /* model input patch edge (cta/preprocess.py:76,99)      */
+#define RIBCA_MAX_TAPS 128     /* largest Gaussian radius accepted by the FIR kernels   */
+#define RIBCA_MAX_PANEL_CH 16  /* largest panel (immune_full has 15 markers)            */
+#define RIBCA_MAX_PANELS 3     /* one immune panel + structure + nerve per predict()    */
+
+typedef void* ribca_stream_t;  /* cudaStream_t */
+
+enum ribca_dtype { RIBCA_U8 = 0, RIBCA_U16 = 1, RIBCA_F32 = 2, RIBCA_I32 = 3 };
+
+/* operand precision of the tensor-core contractions (stage 4) */
+enum ribca_precision {
+  RIBCA_BF16X3 = 0, /* split-bf16, 3 tcgen05 passes (hi*hi + lo*hi + hi*lo), fp32 accumulate: parity mode */
+  RIBCA_BF16X1 = 1, /* single bf16 pass: throughput mode (outside the 1e-3 probability tolerance)          */
+  RIBCA_SIMT_FP32 = 2 /* same contraction on the FP32 pipe (debug cross-check, no tensor cores)             */
+};
+
+const char* ribca_last_error(void);
+int ribca_version(void);
+/* number of kernels this library has launched in the calling process (bench.py `gpu_launches`) */
+long long ribca_launch_count(void);
+
+/* Optional per-kernel-class device timing for roofline reports: between ribca_profile_begin() and
+ * ribca_profile_end() every launch of the classes below is bracketed by CUDA events on its stream.
+ * ribca_profile_end fills, per class, the summed kernel time (ms), the launch count and the
+ * algorithmic work (FLOP for GEMM / attention, bytes for the patch builder). */
+#define RIBCA_PROF_GEMM 0
+#define RIBCA_PROF_ATTENTION 1
+#define RIBCA_PROF_PATCHES 2
+#define RIBCA_PROF_CLASSES 3
+int ribca_profile_begin(void);
+int ribca_profile_end(double* ms, long long* launches, double* work, int n_classes);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 - image normalisation.      replaces ImageProcessor._normalize  cta/preprocess.py:214-239
+ *
+ * Per channel: x = f32(img); bg = G_sigma20(x) (scipy gaussian_filter: axis 0 then axis 1, mode
+ * reflect, float64 accumulate in scipy's tap order, float32 store) ; bg = min(bg, 125);
+ * x = max(x - bg, 0); optional blur G_blur(x); all-non-positive channel -> -1; t = percentile
+ * (numpy 'linear' between the order statistics k_lo, k_hi with weight gamma, all float32);
+ * clip to t when t > 20; out = 2 * x / max(25, max x) - 1.
+ * The tap weights and the order-statistic plan are computed by the host exactly as scipy / numpy
+ * do (so results are bit-identical to the reference) and passed in:
+ *   h_w_bg[0..r_bg]     half kernel, h_w_bg[j] = weight at distance j from the centre
+ *   h_w_blur[0..r_blur] same for the blur; r_blur < 0 disables the blur
+ *   k_lo, k_hi, gamma   np.percentile plan for n = H*W (see host `percentile_plan`)
+ * chan_stats (optional, device, C x 4 floats): [percentile, max after clip, all_non_positive, min(out)].
+ */
+size_t ribca_normalize_workspace_bytes(int C, int H, int W);
+int ribca_normalize(const void* img, int dtype, int C, int H, int W,
+                    const double* h_w_bg, int r_bg, const double* h_w_blur, int r_blur,
+                    long long k_lo, long long k_hi, float gamma,
+                    float* out, float* chan_stats, void* workspace, size_t workspace_bytes,
+                    ribca_stream_t stream);
+
+/* per-channel minimum of a float32 stack (ImageProcessor._move_image_range, cta/preprocess.py:153-157) */
+int ribca_channel_min(const float* img, int C, long long hw, float* min_val, ribca_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2 - label mask -> per-cell statistics.
+ *                 replaces ImageProcessor._cell_pos_dict + process_chunk
+ *                          cta/preprocess.py:159-211, cta/utils.py:272-290
+ * and the reductions every consumer applies to the pixel lists (bbox: cta/utils.py:227,232;
+ * centroid: cta/model.py:785-786; area).  Integer, bit-exact.
+ *
+ * ribca_mask_minmax: out2[0] = min label, out2[1] = max label (device int32[2]).
+ * ribca_cell_stats:  dense tables indexed by label 0..max_id (label 0 = background is skipped):
+ *     bbox[id] = {rmin, rmax, cmin, cmax}, sums[id] = {sum of rows, sum of cols}, count[id].
+ *     The call initialises the tables itself.
+ * ribca_compact_cells: ascending list of the labels with count > 0 and their rows of the tables
+ *     -> ids[n], cbbox[n][4], csums[n][2], ccount[n]; *n_cells (device int32).
+ */
+int ribca_mask_minmax(const int32_t* mask, long long n, int32_t* out2, ribca_stream_t stream);
+int ribca_cell_stats(const int32_t* mask, int H, int W, int max_id, int32_t* bbox,
+                     unsigned long long* sums, int32_t* count, ribca_stream_t stream);
+size_t ribca_compact_workspace_bytes(int max_id);
+int ribca_compact_cells(const int32_t* bbox, const unsigned long long* sums, const int32_t* count,
+                        int max_id, int32_t* ids, int32_t* cbbox, unsigned long long* csums,
+                        int32_t* ccount, int32_t* id_to_index, int32_t* n_cells, void* workspace,
+                        size_t workspace_bytes, ribca_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3 - per-cell patch gather with the soft cell mask.
+ *      replaces crop_cell + smooth (cta/utils.py:226-270) and ImageProcessor._img2patches
+ *      (cta/preprocess.py:76-151) for cell_size = 30 (40 x 40 patch, resize = identity).
+ *
+ * For cell j (label ids[j], bbox cbbox[j]): window (x0,x1,y0,y1) of cta/utils.py:227-235;
+ * s = smooth(mask window == id) in the reference's float32/float64 op order (bit-exact);
+ * value[c] = f32( f64(img[c] - min_val[c]) * f64(s) + f64(min_val[c]) ), zero-padded window;
+ * each requested panel p gets out[p][j][k] = value[h_chan_index[p][k]] or -1 for the first -1
+ * entry (a later -1 selects the last image channel: numpy negative index, quirk Q3).
+ * avg_int[j][c] (optional, float64) = mean of the float64 value over window pixels with label > 0.
+ * windows[j] (optional) = {x0, x1, y0, y1}.
+ *   h_gauss[3][RIBCA_GAUSS_STRIDE]: half kernels of sigma 1, 2, 3 (radius 4, 8, 12) as scipy
+ *   computes them (host numpy), h_gauss[s][j] = weight at distance j.
+ */
+#define RIBCA_GAUSS_STRIDE 16
+int ribca_build_patches(const float* img, const int32_t* mask, int C_img, int H, int W,
+                        const float* min_val, const int32_t* ids, const int32_t* cbbox,
+                        int cell_begin, int n_cells, int n_panels, const int* h_n_ch,
+                        const int* h_chan_index /* [n_panels][RIBCA_MAX_PANEL_CH] */,
+                        float* const* h_out /* n_panels device pointers, each [n_cells][n_ch][40][40] */,
+                        const double* h_gauss, double* avg_int, int32_t* windows,
+                        ribca_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 4 - networks.  replaces VisionTransformer / vit_* and _predict_cell_types' forward +
+ * softmax (cta/model.py:31-88, 397-406) and MaskedAutoencoderViT / MarkerImputer.impute
+ * (cta/markerImputer.py:155-232, 294-329).
+ *
+ * Primitive: C[M,N] (+epilogue) = A[M,K] . W[N,K]^T with split-bf16 operands.
+ *   A, W are stored as two bf16 planes {hi, lo} (x = hi + lo), plane stride a_plane / w_plane
+ *   elements, both K-major (row-major [rows][K]); fp32 accumulate in TMEM.
+ *   epilogue: v = acc + (bias ? bias[col] : 0) + (row_table ? row_table[(row % table_period)*N + col] : 0)
+ *     RIBCA_EPI_STORE    out_f32[row*N+col]  = v
+ *     RIBCA_EPI_RESIDUAL out_f32[row*N+col] += v
+ *     RIBCA_EPI_GELU     out split-bf16 {hi, lo}[row*N+col] = gelu_erf(v), plane stride out_plane
+ */
+enum ribca_epilogue { RIBCA_EPI_STORE = 0, RIBCA_EPI_RESIDUAL = 1, RIBCA_EPI_GELU = 2 };
+int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long long w_plane,
+                         int M, int N, int K, const float* bias, const float* row_table,
+                         int table_period, int epilogue, float* out_f32, void* out_split,
+                         long long out_plane, int precision, ribca_stream_t stream);
+/* x (fp32, n) -> bf16 planes hi / lo */
+int ribca_split_bf16(const float* x, long long n, void* hi, void* lo, ribca_stream_t stream);
+
+/* row LayerNorm(eps) of x[M][D] -> split-bf16 planes (plane stride out_plane elements) */
+int ribca_layernorm_split(const float* x, int M, int D, const float* gamma, const float* beta,
+                          float eps, void* out_split, long long out_plane, ribca_stream_t stream);
+/* multi-head self-attention over qkv[cells][tokens][3][heads][hd] (fp32) -> split-bf16 [M][D] */
+int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head_dim,
+                    void* out_split, long long out_plane, ribca_stream_t stream);
+
+/* Classifier: device-resident weights in the layout produced by the host packer
+ * (multiplexed_image_annotator_b200/engine.py: pack_vit); all offsets in `desc` are element
+ * offsets into `wf32` (fp32 params) or `wsplit` (bf16 planes, plane stride desc->split_plane). */
+typedef struct ribca_block_desc {
+  long long ln1_g, ln1_b, ln2_g, ln2_b;           /* wf32 */
+  long long qkv_b, proj_b, fc1_b, fc2_b;           /* wf32 */
+  long long qkv_w, proj_w, fc1_w, fc2_w;           /* wsplit */
+} ribca_block_desc;
+
+typedef struct ribca_vit_desc {
+  int dim, heads, depth, in_chans, classes, tokens;  /* tokens = 101 */
+  long long split_plane;                             /* elements between the hi and lo plane */
+  long long embed_w;                                 /* wsplit [dim][16*in_chans] */
+  long long embed_table;                             /* wf32 [tokens][dim]: row0 = cls+pos0, row t = bias+pos_t */
+  long long norm_g, norm_b, head_w, head_b;          /* wf32 */
+  ribca_block_desc blocks[16];
+} ribca_vit_desc;
+
+size_t ribca_vit_workspace_bytes(const ribca_vit_desc* desc, int n_cells);
+/* patches [n_cells][in_chans][40][40] fp32 -> probs [n_cells][classes] (softmax) and, optionally, logits */
+int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void* wsplit,
+                      const float* patches, int n_cells, float* probs, float* logits,
+                      void* workspace, size_t workspace_bytes, int precision, ribca_stream_t stream);
+
+typedef struct ribca_mae_desc {
+  int channels;                    /* L = grid rows * cols (7 / 10 / 15) */
+  int enc_dim, enc_heads, enc_depth, dec_dim, dec_heads, dec_depth;
+  long long split_plane;
+  long long embed_w;               /* wsplit [enc_dim][1600] */
+  long long embed_bias, cls_token, pos_embed;            /* wf32: [enc_dim], [enc_dim], [1+L][enc_dim] */
+  long long norm_g, norm_b;
+  long long dec_embed_w;           /* wsplit [dec_dim][enc_dim] */
+  long long dec_embed_b, mask_token, dec_pos_embed;      /* wf32 */
+  long long dec_norm_g, dec_norm_b;
+  long long pred_w;                /* wsplit [1600][dec_dim] */
+  long long pred_b;
+  ribca_block_desc enc_blocks[16];
+  ribca_block_desc dec_blocks[16];
+} ribca_mae_desc;
+
+size_t ribca_mae_workspace_bytes(const ribca_mae_desc* desc, int n_cells);
+/* in-place imputation of the missing channels of patches [n_cells][L][40][40];
+ * h_present[n_present] = ascending positions of the markers that are present. */
+int ribca_mae_impute(const ribca_mae_desc* desc, const float* wf32, const void* wsplit,
+                     float* patches, int n_cells, const int* h_present, int n_present,
+                     void* workspace, size_t workspace_bytes, int precision, ribca_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 5 - vote merge, "Others" threshold, per-type counts.
+ *        replaces Annotator.merge_by_voting + get_void_vote  cta/model.py:481-636, cta/utils.py:143-146
+ *
+ * Up to two probability tables take part (the reference's elif chain never merges three).
+ * Class k of model m is global cell type h_type_of_class[m][k] (index into the 18-entry list of
+ * cta/model.py:97-99, 17 = "Others").  h_vote_rank[type] = position in get_void_vote()'s key order
+ * (tie-break: first maximum in that order for two models; class-index order for one model).
+ * h_type_thresh[18] = cell_type_confidence values; confidence = global threshold.
+ * Outputs: label[n] (uint8 global type), conf[n] (float32, -1 when re-labelled "Others"),
+ * counts[18] (int64, accumulated: caller zeroes).
+ */
+int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_class0,
+                      const float* probs1, int classes1, const int* h_type_of_class1, int n_cells,
+                      const int* h_vote_rank, const float* h_type_thresh, float confidence,
+                      uint8_t* label, float* conf, long long* counts, ribca_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIBCA_B200_H */

@@ -1,0 +1,214 @@
+"""`ImageProcessor`: stages 1-3 of the hot path on the device, behind the reference's interface
+(cta/preprocess.py:25-290: constructor arguments, `transform()`, and the public attributes
+`masks`, `cell_pos_dict`, `intensity_full` that downstream reference code reads).
+
+What changed under the interface: the image stack is normalised by ribca_normalize, the mask is
+reduced to per-cell bbox / sums / area by ribca_cell_stats, and the 40x40 model inputs are built by
+ribca_build_patches straight into device batches - they are handed to `Annotator.predict` in HBM
+instead of being spilled to `<main_dir>/tmp/*.pt` (the tmp directory is still created and wiped so
+`clear_tmp()` keeps working).  Only the panels `predict` consumes are cropped (the reference also
+crops the unused immune panels and deletes them afterwards, quirk Q5).
+"""
+from __future__ import annotations
+
+import os
+from collections.abc import Mapping
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import ops
+from ..io import read_image, read_mask
+from ..parallel import shard_range, world
+from .markerImputer import MarkerImputer
+
+PATCH_CACHE_BYTES = int(os.environ.get("RIBCA_PATCH_CACHE_BYTES", 48 << 30))
+CHUNK_CELLS = int(os.environ.get("RIBCA_CHUNK_CELLS", 8192))
+
+
+class CellPositions(Mapping):
+    """`cell_pos_dict[i]` of the reference ({id: (rows, cols)} in raster order, ids ascending,
+    cta/preprocess.py:159-181) backed by the device cell table: keys, bbox, centroid and area come
+    from the table; the pixel lists of a cell are materialised from its bbox window only when asked."""
+
+    def __init__(self, mask_host: np.ndarray, ids: np.ndarray, bbox: np.ndarray, sums: np.ndarray, count: np.ndarray):
+        self._mask, self.ids, self.bbox, self.sums, self.count = mask_host, ids, bbox, sums, count
+        self._index = None
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __iter__(self):
+        return iter(self._mask.dtype.type(i) for i in self.ids)
+
+    def _row(self, key):
+        if self._index is None:
+            self._index = {int(v): k for k, v in enumerate(self.ids)}
+        return self._index[int(key)]
+
+    def __contains__(self, key):
+        try:
+            self._row(key)
+            return True
+        except (KeyError, TypeError, ValueError):
+            return False
+
+    def __getitem__(self, key):
+        k = self._row(key)
+        r0, r1, c0, c1 = (int(v) for v in self.bbox[k])
+        rr, cc = np.nonzero(self._mask[r0:r1 + 1, c0:c1 + 1] == int(key))
+        return (rr + r0).tolist(), (cc + c0).tolist()
+
+    def centroid(self, key):
+        """(mean row, mean col) = np.mean of the lists, without materialising them."""
+        k = self._row(key)
+        return float(self.sums[k, 0]) / float(self.count[k]), float(self.sums[k, 1]) / float(self.count[k])
+
+
+class ImageProcessor(object):
+    def __init__(self, csv_path, parser, main_path, device, batch_id='', infer=True, normalization=True, blur=0,
+                 amax=100, cell_size=30, logger=None, n_jobs=0) -> None:
+        df = pd.read_csv(csv_path)
+        self.image_paths = df['image_path']
+        self.mask_paths = df['mask_path']
+        assert len(self.image_paths) == len(self.mask_paths)
+        self.logger = logger
+        self._n_images = len(self.image_paths)
+        self.logger.log("Number of images: {}.".format(self._n_images))
+        self.main_dir = main_path
+        self.save_path = os.path.join(self.main_dir, "tmp")
+        self.batch_id = batch_id
+        self.normalization = normalization
+        self.blur = blur
+        self.amax = amax
+        self.parser = parser
+        self.cell_pos_dict = []
+        self.intensity_full = []
+        os.makedirs(self.save_path, exist_ok=True)
+        for f in os.listdir(self.save_path):
+            fp = os.path.join(self.save_path, f)
+            if os.path.isfile(fp):
+                os.remove(fp)
+        self.infer = infer
+        self.masks = []
+        if str(device).startswith("cpu"):
+            raise RuntimeError("the B200 build has no CPU path: pass device='cuda' (the reference's CPU path is the oracle)")
+        self.device = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        if int(cell_size) != 30:
+            raise NotImplementedError("cell_size != 30 (patch resampling) is not built yet; see DESIGN.md 'next'")
+        self.scale = cell_size / 30.0
+        self.n_jobs = n_jobs
+        # device-side state per image
+        self.images_dev, self.masks_dev, self.cells, self.min_val = [], [], [], []
+        self.patches = []          # per image: {panel: tensor} for this rank's cell range, or None (streamed)
+        self.cell_range = []       # per image: (lo, hi) cells owned by this rank
+        self._imputers = {}
+        self.logger.log("\n")
+        self.logger.log("Starting image processing...")
+
+    # ---- panels ------------------------------------------------------------------------------------
+    def predicted_panels(self):
+        """Panels `Annotator.predict` consumes: full > extended > base, then structure, nerve
+        (reference model.py:246-349)."""
+        idx = self.parser.indices
+        out = [p for p in ("immune_full", "immune_extended", "immune_base") if idx.get(p)][:1]
+        out += [p for p in ("structure", "nerve_cell") if idx.get(p)]
+        return out
+
+    def _imputer_for(self, panel):
+        """preprocess.py:267-281: imputation only for immune panels with a missing marker and infer=True."""
+        index = self.parser.indices[panel]
+        if not self.infer or -1 not in index or panel == "structure" or panel == "nerve":
+            return None
+        if panel not in self._imputers:
+            present = [i for i, x in enumerate(index) if x != -1]
+            self._imputers[panel] = MarkerImputer(present, self.device, panel)
+            print("Imputer for {} is created".format(panel))
+            msg = "Imputer for {} is created. Marker(s) ".format(panel)
+            for k, ch in enumerate(index):
+                if ch == -1:
+                    msg += "{} ".format(self.parser.panels[panel][k])
+            self.logger.log(msg + "are imputed.")
+        return self._imputers[panel]
+
+    # ---- reference-named stage entry points (device tensors in, device tensors out) -----------------
+    def _normalize(self, img, blur=0, amax=100):
+        """cta/preprocess.py:214-239 on the device.  Accepts a numpy array or a CUDA tensor."""
+        t = torch.from_numpy(np.ascontiguousarray(img)).to(self.device) if isinstance(img, np.ndarray) else img
+        return ops.normalize(t.contiguous(), blur, amax)
+
+    def _cell_pos_dict(self, mask, n_jobs=0):
+        """cta/preprocess.py:159-211: returns the lazy mapping (n_jobs is accepted and ignored)."""
+        host = np.ascontiguousarray(mask.cpu().numpy() if isinstance(mask, torch.Tensor) else mask)
+        dev = torch.from_numpy(host.astype(np.int32)).to(self.device)
+        tab = ops.cell_stats(dev)
+        return self._positions(host, tab)
+
+    @staticmethod
+    def _positions(mask_host, tab):
+        return CellPositions(mask_host, tab.ids.cpu().numpy(), tab.bbox.cpu().numpy(), tab.sums.cpu().numpy(),
+                             tab.count.cpu().numpy())
+
+    def _move_image_range(self, image):
+        """cta/preprocess.py:153-157."""
+        mn = ops.channel_min(image)
+        return mn.view(-1, 1, 1), image - mn.view(-1, 1, 1)
+
+    def patch_chunks(self, i, panels=None, chunk=None, want_intensity=False):
+        """Yield (lo, hi, {panel: (n, C_p, 40, 40) float32 cuda}, avg_int or None) over this rank's
+        cells of image i - `_img2patches` (cta/preprocess.py:76-151) without the disk spill."""
+        panels = self.predicted_panels() if panels is None else panels
+        chunk = chunk or CHUNK_CELLS
+        lo, hi = self.cell_range[i]
+        idx = [self.parser.indices[p] for p in panels]
+        for a in range(lo, hi, chunk):
+            b = min(a + chunk, hi)
+            outs, avg, _ = ops.build_patches(self.images_dev[i], self.masks_dev[i], self.min_val[i], self.cells[i], idx,
+                                             a, b - a, want_intensity=want_intensity)
+            batch = dict(zip(panels, outs))
+            for p in panels:
+                imp = self._imputer_for(p)
+                if imp is not None:
+                    imp.impute(batch[p], 64)
+            yield a, b, batch, avg
+
+    # ---- the reference's driver ----------------------------------------------------------------------
+    def transform(self):
+        rank, nranks = world()
+        for i, (image_path, mask_path) in enumerate(zip(self.image_paths, self.mask_paths)):
+            image = read_image(image_path)
+            mask = read_mask(mask_path)                       # 2-D, int32 (preprocess.py:246-250)
+            img_dev = torch.from_numpy(image).to(self.device, non_blocking=True)
+            mask_dev = torch.from_numpy(mask).to(self.device, non_blocking=True)
+            if self.normalization:
+                img_dev = ops.normalize(img_dev, self.blur, self.amax)
+            elif img_dev.dtype != torch.float32:
+                img_dev = img_dev.to(torch.float32)
+            self.masks.append(mask)
+            tab = ops.cell_stats(mask_dev)
+            self.images_dev.append(img_dev)
+            self.masks_dev.append(mask_dev)
+            self.cells.append(tab)
+            self.min_val.append(ops.channel_min(img_dev))
+            self.cell_pos_dict.append(self._positions(mask, tab))
+            self.cell_range.append(shard_range(tab.n, rank, nranks))
+            panels = self.predicted_panels()
+            lo, hi = self.cell_range[i]
+            per_cell = sum(len(self.parser.indices[p]) for p in panels) * 40 * 40 * 4
+            keep = (hi - lo) * per_cell <= PATCH_CACHE_BYTES
+            inten = torch.empty((hi - lo, img_dev.shape[0]), dtype=torch.float64, device=self.device)
+            kept = {p: [] for p in panels}
+            for a, b, batch, avg in self.patch_chunks(i, panels if keep else [], want_intensity=True):
+                inten[a - lo:b - lo] = avg
+                for p in batch:
+                    kept[p].append(batch[p])
+            self.patches.append({p: torch.cat(v) if v else torch.empty((0, len(self.parser.indices[p]), 40, 40), device=self.device)
+                                 for p, v in kept.items()} if keep else None)
+            # preprocess.py:144-149,284-285: (avg_int + 1) / 2, all image channels, first applied panel
+            self.intensity_full.append(self._gather_rows((inten + 1) / 2, tab.n, lo, hi).cpu().numpy())
+
+    @staticmethod
+    def _gather_rows(local, n_total, lo, hi):
+        from ..parallel import all_gather_rows
+        return all_gather_rows(local, n_total, lo, hi)

@@ -1,0 +1,73 @@
+// Error reporting, version and launch accounting for libribca_b200.so.
+#include "common.cuh"
+
+#include <atomic>
+#include <vector>
+
+namespace ribca {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel-class timing (bench.py's roofline leg) ----------------------------------
+// When enabled, the launch helpers of the dominant kernels bracket each launch with CUDA events on
+// the launching stream; ribca_profile_end() synchronises and sums the elapsed times per class.
+struct ProfSpan { int cls; cudaEvent_t a, b; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_spans;
+
+bool profiling() { return g_prof_on; }
+
+void prof_begin_span(int cls, double work, cudaStream_t st) {
+  ProfSpan s{cls, nullptr, nullptr, work};
+  if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+  cudaEventRecord(s.a, st);
+  g_spans.push_back(s);
+}
+void prof_end_span(cudaStream_t st) {
+  if (!g_spans.empty()) cudaEventRecord(g_spans.back().b, st);
+}
+
+}  // namespace ribca
+
+extern "C" {
+
+const char* ribca_last_error(void) { return ribca::g_err; }
+int ribca_version(void) { return 100; }
+long long ribca_launch_count(void) { return ribca::g_launches.load(std::memory_order_relaxed); }
+
+int ribca_profile_begin(void) {
+  ribca::g_spans.clear();
+  ribca::g_prof_on = true;
+  return RIBCA_OK;
+}
+
+int ribca_profile_end(double* ms, long long* launches, double* work, int n_classes) {
+  ribca::g_prof_on = false;
+  for (int c = 0; c < n_classes; ++c) { ms[c] = 0.0; launches[c] = 0; work[c] = 0.0; }
+  int rc = RIBCA_OK;
+  for (auto& s : ribca::g_spans) {
+    float t = 0.f;
+    if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+      if (s.cls >= 0 && s.cls < n_classes) { ms[s.cls] += t; launches[s.cls] += 1; work[s.cls] += s.work; }
+    } else {
+      rc = RIBCA_ECUDA;
+    }
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  ribca::g_spans.clear();
+  if (rc != RIBCA_OK) ribca::set_error("ribca_profile_end: event timing failed");
+  return rc;
+}
+
+}  // extern "C"

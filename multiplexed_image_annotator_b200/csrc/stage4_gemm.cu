@@ -1,0 +1,495 @@
+// Stage 4 primitive: C[M,N] = A[M,K] . W[N,K]^T (+ fused epilogue) on the 5th-gen tensor cores.
+//
+// The reference runs its ViT / MAE linears as fp32 PyTorch GEMMs (cta/model.py:397-406,
+// cta/markerImputer.py:186-232).  A single bf16 pass cannot hold the 1e-3 probability tolerance
+// (SURVEY section 7), so operands are stored as two bf16 planes x = hi + lo and the product is
+// accumulated in fp32 TMEM as  lo.hi + hi.lo + hi.hi  (three tcgen05 passes over K, "bf16x3").
+// Because the split is a data layout, the kernel itself is a plain K-major bf16 GEMM whose K loop
+// walks a list of (A plane, W plane) pairs; bf16x1 just walks one pair.
+//
+// Kernel shape (sm_100a, cta_group::1):
+//   persistent grid, one CTA per SM, 192 threads = 6 warps
+//     warp 0     TMA producer: 3-D tensor maps (K, rows, plane), 128B swizzle, box 64 x rows x 1,
+//                4-stage shared ring, mbarrier expect_tx; out-of-range K / rows are zero-filled by
+//                the TMA unit, so K need not be a multiple of 64 nor M of 128
+//     warp 1     allocates 512 TMEM columns, one lane issues tcgen05.mma (M=128, N=BN<=256, K=16)
+//                from shared-memory descriptors; tcgen05.commit releases ring slots / publishes
+//                the accumulator
+//     warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias / row table / residual / GELU
+//                -> global; TMEM is double-buffered (2 x 256 columns) so the epilogue of tile t
+//                overlaps the main loop of tile t+1
+//   tiles are ordered m-major so the CTAs of one wave share A rows through L2 and W stays L2-resident.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace ribca {
+
+constexpr int BM = 128;
+constexpr int BK = 64;              // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kMaxBN = 256;
+constexpr int kGemmThreads = 192;
+constexpr int kABytes = BM * BK * 2;            // 16 KB
+constexpr int kBBytesMax = kMaxBN * BK * 2;     // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kTmemCols = 512;
+
+struct GemmEpilogue {
+  const float* bias;        // [N] or null
+  const float* row_table;   // [table_period][N] or null
+  int table_period;
+  int mode;                 // ribca_epilogue
+  float* out_f32;           // [M][N]
+  __nv_bfloat16* out_hi;    // split output planes (GELU mode)
+  __nv_bfloat16* out_lo;
+};
+
+struct GemmShape {
+  int M, N, K;
+  int BN;                   // N tile (multiple of 16, <= 256, divides N)
+  int n_pass;               // 3 (bf16x3) or 1
+  int a_plane[3];           // plane index of A per pass
+  int w_plane[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (bf16 in, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) ;
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups ; [46,48) version = 1 ;
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// K-major A and B (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t make_instr_desc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const GemmShape shp, const GemmEpilogue epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int BN = shp.BN;
+  const int n_tiles_n = shp.N / BN;
+  const int n_tiles_m = (shp.M + BM - 1) / BM;
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_kb = (shp.K + BK - 1) / BK;
+  const int n_iter = n_kb * shp.n_pass;
+  const uint32_t stage_tx = (uint32_t)(kABytes + BN * BK * 2);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        for (int it = 0; it < n_iter; ++it) {
+          const int pass = it / n_kb, kb = it - pass * n_kb;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, shp.a_plane[pass]);
+          tma_load_3d(sb, &tmap_w, &full_bar[stage], kb * BK, n0, shp.w_plane[pass]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(BN);
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t use = (uint32_t)(local >> 1);
+        mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);      // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kMaxBN);
+        for (int it = 0; it < n_iter; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
+            const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
+            umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                  // slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[buf]);                      // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
+    int local = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t use = (uint32_t)(local >> 1);
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      mbar_wait(&tmem_full[buf], use & 1u);
+      tcgen05_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < shp.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
+      const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)c, v);
+        if (row_ok) {
+          const int col = n0 + c;
+          if (epi.bias) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q);
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+          }
+          if (table_row) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(table_row + col) + q);
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+          }
+          const long long o = (long long)row * shp.N + col;
+          if (epi.mode == RIBCA_EPI_GELU) {
+            __align__(16) __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_bf16(gelu_erf(v[i]), hi[i], lo[i]);
+            uint4* ph = reinterpret_cast<uint4*>(epi.out_hi + o);
+            uint4* pl = reinterpret_cast<uint4*>(epi.out_lo + o);
+            ph[0] = reinterpret_cast<const uint4*>(hi)[0]; ph[1] = reinterpret_cast<const uint4*>(hi)[1];
+            pl[0] = reinterpret_cast<const uint4*>(lo)[0]; pl[1] = reinterpret_cast<const uint4*>(lo)[1];
+          } else {
+            float4* po = reinterpret_cast<float4*>(epi.out_f32 + o);
+            if (epi.mode == RIBCA_EPI_RESIDUAL) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 x = po[q];
+                v[4 * q] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Same contraction on the FP32 pipe (x = hi + lo reconstructed exactly, fp32 FMA accumulate):
+// the on-device cross-check of the tensor-core kernel and the RIBCA_SIMT_FP32 precision mode.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST = 64, SK = 16;
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, long long a_plane, const __nv_bfloat16* __restrict__ W,
+                 long long w_plane, const GemmShape shp, const GemmEpilogue epi) {
+  __shared__ float As[SK][ST + 1];
+  __shared__ float Ws[SK][ST + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < shp.K; k0 += SK) {
+    for (int idx = threadIdx.x; idx < ST * SK; idx += 256) {
+      const int r = idx / SK, k = idx % SK;
+      float a = 0.f, w = 0.f;
+      if (m0 + r < shp.M && k0 + k < shp.K) {
+        const long long o = (long long)(m0 + r) * shp.K + k0 + k;
+        a = __bfloat162float(A[o]) + __bfloat162float(A[a_plane + o]);
+      }
+      if (n0 + r < shp.N && k0 + k < shp.K) {
+        const long long o = (long long)(n0 + r) * shp.K + k0 + k;
+        w = __bfloat162float(W[o]) + __bfloat162float(W[w_plane + o]);
+      }
+      As[k][r] = a;
+      Ws[k][r] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= shp.M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= shp.N) continue;
+      float v = acc[i][j];
+      if (epi.bias) v += epi.bias[col];
+      if (epi.row_table) v += epi.row_table[(long long)(row % epi.table_period) * shp.N + col];
+      const long long o = (long long)row * shp.N + col;
+      if (epi.mode == RIBCA_EPI_GELU) {
+        split_bf16(gelu_erf(v), epi.out_hi[o], epi.out_lo[o]);
+      } else if (epi.mode == RIBCA_EPI_RESIDUAL) {
+        epi.out_f32[o] += v;
+      } else {
+        epi.out_f32[o] = v;
+      }
+    }
+  }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) split_bf16(x[i], hi[i], lo[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 3-D map over a split operand: dims (K, rows, 2 planes), box (64, box_rows, 1), 128B swizzle
+static int make_operand_map(CUtensorMap* map, const void* base, long long plane_elems, int rows, int K, int box_rows) {
+  auto encode = get_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return RIBCA_ECUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_elems * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d box_rows=%d plane=%lld", (int)r, rows, K, box_rows, plane_elems);
+    return RIBCA_ECUDA;
+  }
+  return RIBCA_OK;
+}
+
+int pick_bn(int N) {
+  for (int bn = kMaxBN; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+int gemm_launch(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
+                const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
+                void* out_split, long long out_plane, int precision, cudaStream_t stream) {
+  RIBCA_REQUIRE(A && W, "gemm: null operand");
+  RIBCA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  RIBCA_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm: N=%d must be a multiple of 16 and K=%d of 8", N, K);
+  RIBCA_REQUIRE(epilogue == RIBCA_EPI_GELU ? (out_split != nullptr) : (out_f32 != nullptr), "gemm: output is null");
+  RIBCA_REQUIRE(!row_table || table_period > 0, "gemm: row table needs a period");
+  RIBCA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                    (a_plane * 2) % 16 == 0 && (w_plane * 2) % 16 == 0,
+                "gemm: operands must be 16-byte aligned");
+  GemmShape shp;
+  memset(&shp, 0, sizeof(shp));
+  shp.M = M; shp.N = N; shp.K = K;
+  shp.BN = pick_bn(N);
+  RIBCA_REQUIRE(shp.BN > 0, "gemm: no N tile for N=%d", N);
+  if (precision == RIBCA_BF16X1) {
+    shp.n_pass = 1; shp.a_plane[0] = 0; shp.w_plane[0] = 0;
+  } else {
+    shp.n_pass = 3;                       // small terms first, then hi.hi
+    shp.a_plane[0] = 1; shp.w_plane[0] = 0;
+    shp.a_plane[1] = 0; shp.w_plane[1] = 1;
+    shp.a_plane[2] = 0; shp.w_plane[2] = 0;
+  }
+  GemmEpilogue epi;
+  epi.bias = bias; epi.row_table = row_table; epi.table_period = table_period > 0 ? table_period : 1;
+  epi.mode = epilogue; epi.out_f32 = out_f32;
+  epi.out_hi = static_cast<__nv_bfloat16*>(out_split);
+  epi.out_lo = out_split ? static_cast<__nv_bfloat16*>(out_split) + out_plane : nullptr;
+
+  if (precision == RIBCA_SIMT_FP32) {
+    dim3 grid((N + ST - 1) / ST, (M + ST - 1) / ST);
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), a_plane,
+                                               static_cast<const __nv_bfloat16*>(W), w_plane, shp, epi);
+    RIBCA_LAUNCH_CHECK("gemm_simt_kernel");
+    return RIBCA_OK;
+  }
+  RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1, "gemm: unknown precision %d", precision);
+  CUtensorMap map_a, map_w;
+  RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM));
+  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN));
+  static bool attr_set = false;
+  if (!attr_set) {
+    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
+                         "cudaFuncSetAttribute(gemm_tcgen05_kernel)"));
+    attr_set = true;
+  }
+  const int n_tiles = ((M + BM - 1) / BM) * (N / shp.BN);
+  const int grid = std::min(n_tiles, num_sms());
+  const bool prof = profiling();
+  if (prof) prof_begin_span(RIBCA_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream);
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, shp, epi);
+  if (prof) prof_end_span(stream);
+  RIBCA_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return RIBCA_OK;
+}
+
+int split_launch(const float* x, long long n, void* hi, void* lo, cudaStream_t stream) {
+  if (n <= 0) return RIBCA_OK;
+  int blocks = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
+  split_bf16_kernel<<<blocks, 256, 0, stream>>>(x, n, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
+  RIBCA_LAUNCH_CHECK("split_bf16_kernel");
+  return RIBCA_OK;
+}
+
+}  // namespace ribca
+
+using namespace ribca;
+
+extern "C" {
+
+int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
+                         const float* bias, const float* row_table, int table_period, int epilogue,
+                         float* out_f32, void* out_split, long long out_plane, int precision,
+                         ribca_stream_t stream) {
+  return gemm_launch(A, a_plane, W, w_plane, M, N, K, bias, row_table, table_period, epilogue, out_f32, out_split,
+                     out_plane, precision, as_stream(stream));
+}
+
+int ribca_split_bf16(const float* x, long long n, void* hi, void* lo, ribca_stream_t stream) {
+  RIBCA_REQUIRE(x && hi && lo, "ribca_split_bf16: null pointer");
+  return split_launch(x, n, hi, lo, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,522 @@
+// Stage 4: the ViT classifiers and the MAE marker imputer, built on the split-bf16 tcgen05 GEMM.
+// Replaces VisionTransformer / vit_* + softmax (reference cta/model.py:31-88, 397-406) and
+// MaskedAutoencoderViT.forward / MarkerImputer.impute (cta/markerImputer.py:155-232, 294-329).
+//
+// Activations between kernels:  residual stream x fp32 [M][D] (M = cells * tokens);
+// every GEMM A-operand is produced directly in split-bf16 planes {hi, lo} by the kernel before it
+// (im2col, LayerNorm, attention, GELU epilogue), so no separate conversion pass touches HBM.
+// Attention (3-12 % of the FLOPs at 101 tokens) runs on the FP32 pipe with K/V staged in shared memory.
+#include "common.cuh"
+
+namespace ribca {
+
+int gemm_launch(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
+                const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
+                void* out_split, long long out_plane, int precision, cudaStream_t stream);
+
+typedef __nv_bfloat16 bf16;
+
+// ---- patches -> patch-embed A operand ---------------------------------------------------------
+// A[(cell*101 + 1 + py*10 + px)][c*16 + ky*4 + kx] = patch[cell][c][py*4+ky][px*4+kx]; row cell*101 = 0
+__global__ void __launch_bounds__(256)
+im2col_split_kernel(const float* __restrict__ patches, int n_cells, int C, bf16* __restrict__ a_hi,
+                    bf16* __restrict__ a_lo) {
+  const int Kpe = 16 * C;
+  const long long total = (long long)n_cells * C * 40 * 10;       // one float4 (4 kx) per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int px = (int)(t % 10);
+    const int y = (int)((t / 10) % 40);
+    const int c = (int)((t / 400) % C);
+    const long long cell = t / (400ll * C);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(patches) + t);
+    const long long row = cell * 101 + 1 + (y >> 2) * 10 + px;
+    const long long o = row * Kpe + c * 16 + (y & 3) * 4;
+    bf16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(a_hi + o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(a_lo + o) = *reinterpret_cast<const uint2*>(l);
+  }
+  // class-token rows are all-zero A rows (their value comes from the epilogue's row table)
+  const long long ztotal = (long long)n_cells * Kpe;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ztotal; t += stride) {
+    const long long cell = t / Kpe;
+    const long long o = cell * 101 * Kpe + (t - cell * Kpe);
+    a_hi[o] = __float2bfloat16_rn(0.0f);
+    a_lo[o] = __float2bfloat16_rn(0.0f);
+  }
+}
+
+// ---- LayerNorm -> split-bf16 ------------------------------------------------------------------
+// one warp per row, D % 4 == 0, D <= 1024; fp32 two-pass statistics
+__global__ void __launch_bounds__(256)
+layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nv = D >> 2;                          // float4 per row
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+    float4 v[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) { v[i] = xr[idx]; sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+        bf16 h[4], l[4];
+        split_bf16((v[i].x - mean) * rstd * g.x + b.x, h[0], l[0]);
+        split_bf16((v[i].y - mean) * rstd * g.y + b.y, h[1], l[1]);
+        split_bf16((v[i].z - mean) * rstd * g.z + b.z, h[2], l[2]);
+        split_bf16((v[i].w - mean) * rstd * g.w + b.w, h[3], l[3]);
+        const long long o = (long long)row * D + 4 * idx;
+        *reinterpret_cast<uint2*>(o_hi + o) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(o_lo + o) = *reinterpret_cast<const uint2*>(l);
+      }
+    }
+  }
+}
+
+// ---- multi-head self-attention ----------------------------------------------------------------
+// one CTA per (cell, head); thread t owns query row t; K and V of the head live in shared memory.
+// two passes over the keys (row max, then exp / sum / PV) keep the softmax in exact fp32.
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_kernel(const float* __restrict__ qkv, int tokens, int heads, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+  extern __shared__ float kv[];                   // K [tokens][HD], V [tokens][HD]
+  float* Ks = kv;
+  float* Vs = kv + tokens * HD;
+  const int cell = blockIdx.x / heads, head = blockIdx.x - cell * heads;
+  const int D = heads * HD;
+  const float* base = qkv + (long long)cell * tokens * 3 * D;
+  constexpr int V4 = HD / 4;
+  for (int idx = threadIdx.x; idx < tokens * V4; idx += blockDim.x) {
+    const int t = idx / V4, d4 = idx - t * V4;
+    const float4* rowp = reinterpret_cast<const float4*>(base + (long long)t * 3 * D + head * HD);
+    reinterpret_cast<float4*>(Ks)[idx] = __ldg(rowp + (D >> 2) + d4);
+    reinterpret_cast<float4*>(Vs)[idx] = __ldg(rowp + 2 * (D >> 2) + d4);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= tokens) return;
+  const float scale = 1.0f / sqrtf((float)HD);
+  float q[HD];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(base + (long long)t * 3 * D + head * HD);
+#pragma unroll
+    for (int d4 = 0; d4 < V4; ++d4) {
+      const float4 v = __ldg(qp + d4);
+      q[4 * d4] = v.x * scale; q[4 * d4 + 1] = v.y * scale; q[4 * d4 + 2] = v.z * scale; q[4 * d4 + 3] = v.w * scale;
+    }
+  }
+  float mx = -INFINITY;
+  for (int j = 0; j < tokens; ++j) {
+    const float4* kp = reinterpret_cast<const float4*>(Ks + j * HD);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < V4; ++d4) {
+      const float4 k = kp[d4];
+      s = fmaf(q[4 * d4], k.x, s); s = fmaf(q[4 * d4 + 1], k.y, s); s = fmaf(q[4 * d4 + 2], k.z, s); s = fmaf(q[4 * d4 + 3], k.w, s);
+    }
+    mx = fmaxf(mx, s);
+  }
+  float o[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+  float denom = 0.f;
+  for (int j = 0; j < tokens; ++j) {
+    const float4* kp = reinterpret_cast<const float4*>(Ks + j * HD);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < V4; ++d4) {
+      const float4 k = kp[d4];
+      s = fmaf(q[4 * d4], k.x, s); s = fmaf(q[4 * d4 + 1], k.y, s); s = fmaf(q[4 * d4 + 2], k.z, s); s = fmaf(q[4 * d4 + 3], k.w, s);
+    }
+    const float p = expf(s - mx);
+    denom += p;
+    const float4* vp = reinterpret_cast<const float4*>(Vs + j * HD);
+#pragma unroll
+    for (int d4 = 0; d4 < V4; ++d4) {
+      const float4 v = vp[d4];
+      o[4 * d4] = fmaf(p, v.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(p, v.y, o[4 * d4 + 1]);
+      o[4 * d4 + 2] = fmaf(p, v.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(p, v.w, o[4 * d4 + 3]);
+    }
+  }
+  const float inv = 1.0f / denom;
+  const long long ob = ((long long)cell * tokens + t) * D + head * HD;
+#pragma unroll
+  for (int d4 = 0; d4 < V4; ++d4) {
+    bf16 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_bf16(o[4 * d4 + e] * inv, h[e], l[e]);
+    *reinterpret_cast<uint2*>(o_hi + ob + 4 * d4) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(o_lo + ob + 4 * d4) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// ---- final LayerNorm on the class token + head + softmax --------------------------------------
+// one warp per cell (model.py:61-62 + timm forward_head + softmax(dim=1) of model.py:404)
+__global__ void __launch_bounds__(256)
+head_softmax_kernel(const float* __restrict__ x, int n_cells, int tokens, int D, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, const float* __restrict__ head_w,
+                    const float* __restrict__ head_b, int classes, float* __restrict__ probs, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (cell >= n_cells) return;
+  const float* xr = x + (long long)cell * tokens * D;
+  float v[24];                                   // D <= 768
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const int d = lane + 32 * i; v[i] = d < D ? xr[d] : 0.f; sum += v[i]; }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const int d = lane + 32 * i; if (d < D) { const float a = v[i] - mean; sq += a * a; } }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const int d = lane + 32 * i; v[i] = d < D ? (v[i] - mean) * rstd * __ldg(gamma + d) + __ldg(beta + d) : 0.f; }
+  float lg[16];
+  for (int k = 0; k < classes; ++k) {
+    const float* w = head_w + (long long)k * D;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { const int d = lane + 32 * i; if (d < D) acc = fmaf(v[i], __ldg(w + d), acc); }
+    lg[k] = warp_sum(acc) + __ldg(head_b + k);
+  }
+  if (lane == 0) {
+    float mx = lg[0];
+    for (int k = 1; k < classes; ++k) mx = fmaxf(mx, lg[k]);
+    float e[16], s = 0.f;
+    for (int k = 0; k < classes; ++k) { e[k] = expf(lg[k] - mx); s += e[k]; }
+    for (int k = 0; k < classes; ++k) {
+      probs[(long long)cell * classes + k] = e[k] / s;
+      if (logits) logits[(long long)cell * classes + k] = lg[k];
+    }
+  }
+}
+
+// ---- MAE glue ---------------------------------------------------------------------------------
+struct PresentList { int n; int idx[RIBCA_MAX_PANEL_CH]; int rank[RIBCA_MAX_PANEL_CH]; };
+
+// encoder A operand: row (cell, 0) = 0, row (cell, 1+i) = the 1600 pixels of channel present[i]
+__global__ void __launch_bounds__(256)
+mae_tiles_split_kernel(const float* __restrict__ patches, int n_cells, int L, const __grid_constant__ PresentList pl,
+                       bf16* __restrict__ a_hi, bf16* __restrict__ a_lo) {
+  const int Te = pl.n + 1;
+  const long long total = (long long)n_cells * Te * 400;          // float4 units
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int q = (int)(t % 400);
+    const int tok = (int)((t / 400) % Te);
+    const long long cell = t / (400ll * Te);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tok > 0) v = __ldg(reinterpret_cast<const float4*>(patches + (cell * L + pl.idx[tok - 1]) * 1600ll) + q);
+    bf16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    const long long o = (cell * Te + tok) * 1600ll + 4 * q;
+    *reinterpret_cast<uint2*>(a_hi + o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(a_lo + o) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// row table of the encoder patch-embed epilogue: row 0 = cls + pos[0], row 1+i = bias + pos[1+present[i]]
+__global__ void mae_enc_table_kernel(const float* __restrict__ cls, const float* __restrict__ bias,
+                                     const float* __restrict__ pos, int D, const __grid_constant__ PresentList pl,
+                                     float* __restrict__ table) {
+  const int Te = pl.n + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Te * D; i += gridDim.x * blockDim.x) {
+    const int tok = i / D, d = i - tok * D;
+    table[i] = tok == 0 ? cls[d] + pos[d] : bias[d] + pos[(1 + pl.idx[tok - 1]) * D + d];
+  }
+}
+
+// decoder input (markerImputer.py:208-219): kept tokens back at their positions, mask token elsewhere, + pos
+__global__ void __launch_bounds__(256)
+mae_decoder_input_kernel(const float* __restrict__ emb, const float* __restrict__ mask_token,
+                         const float* __restrict__ dpos, int n_cells, int L, int D,
+                         const __grid_constant__ PresentList pl, float* __restrict__ xd) {
+  const int Te = pl.n + 1, Td = L + 1;
+  const long long total = (long long)n_cells * Td * D;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int d = (int)(t % D);
+    const int tok = (int)((t / D) % Td);
+    const long long cell = t / ((long long)D * Td);
+    float v;
+    if (tok == 0) v = emb[(cell * Te) * D + d];
+    else {
+      const int rk = pl.rank[tok - 1];
+      v = rk >= 0 ? emb[(cell * Te + 1 + rk) * D + d] : mask_token[d];
+    }
+    xd[t] = v + dpos[tok * D + d];
+  }
+}
+
+// blend of markerImputer.py:312-316: predicted tiles replace the missing channels only
+__global__ void __launch_bounds__(256)
+mae_scatter_kernel(const float* __restrict__ pred, int n_cells, int L, const __grid_constant__ PresentList pl,
+                   float* __restrict__ patches) {
+  const int Td = L + 1;
+  const long long total = (long long)n_cells * L * 400;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int q = (int)(t % 400);
+    const int c = (int)((t / 400) % L);
+    const long long cell = t / (400ll * L);
+    if (pl.rank[c] >= 0) continue;
+    reinterpret_cast<float4*>(patches + (cell * L + c) * 1600ll)[q] =
+        reinterpret_cast<const float4*>(pred + (cell * Td + 1 + c) * 1600ll)[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+static int grid_for(long long work_items, int per_block) {
+  return (int)std::min<long long>((work_items + per_block - 1) / per_block, (long long)num_sms() * 16);
+}
+
+int layernorm_launch(const float* x, int M, int D, const float* g, const float* b, float eps, void* out_split,
+                     long long out_plane, cudaStream_t st) {
+  RIBCA_REQUIRE(D % 4 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 4 and <= 1024", D);
+  if (M <= 0) return RIBCA_OK;
+  bf16* hi = static_cast<bf16*>(out_split);
+  layernorm_split_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, M, D, g, b, eps, hi, hi + out_plane);
+  RIBCA_LAUNCH_CHECK("layernorm_split_kernel");
+  return RIBCA_OK;
+}
+
+template <int HD>
+static int attention_launch_hd(const float* qkv, int cells, int tokens, int heads, bf16* hi, bf16* lo, cudaStream_t st) {
+  const size_t smem = (size_t)2 * tokens * HD * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * HD * 4),
+                         "cudaFuncSetAttribute(attention_kernel)"));
+    attr_set = true;
+  }
+  const int threads = (tokens + 31) / 32 * 32;
+  const bool prof = profiling();
+  if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * HD, st);
+  attention_kernel<HD><<<cells * heads, threads, smem, st>>>(qkv, tokens, heads, hi, lo);
+  if (prof) prof_end_span(st);
+  RIBCA_LAUNCH_CHECK("attention_kernel");
+  return RIBCA_OK;
+}
+
+int attention_launch(const float* qkv, int cells, int tokens, int heads, int hd, void* out_split, long long out_plane,
+                     cudaStream_t st) {
+  RIBCA_REQUIRE(tokens > 0 && tokens <= 128, "attention: tokens=%d outside [1,128]", tokens);
+  if (cells <= 0) return RIBCA_OK;
+  bf16* hi = static_cast<bf16*>(out_split);
+  bf16* lo = hi + out_plane;
+  switch (hd) {
+    case 12: return attention_launch_hd<12>(qkv, cells, tokens, heads, hi, lo, st);
+    case 24: return attention_launch_hd<24>(qkv, cells, tokens, heads, hi, lo, st);
+    case 32: return attention_launch_hd<32>(qkv, cells, tokens, heads, hi, lo, st);
+    case 48: return attention_launch_hd<48>(qkv, cells, tokens, heads, hi, lo, st);
+    case 64: return attention_launch_hd<64>(qkv, cells, tokens, heads, hi, lo, st);
+    default: set_error("attention: unsupported head_dim %d", hd); return RIBCA_EUNSUPPORTED;
+  }
+}
+
+struct BlockBuffers {
+  float* x;          // [M][D]
+  bf16* a;           // split [2][M][D]
+  float* qkv;        // [M][3D]
+  bf16* h;           // split [2][M][4D]
+};
+
+// timm Block x depth: x += proj(attn(LN1 x)); x += fc2(gelu(fc1(LN2 x)))
+static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int heads, int cells, int tokens,
+                      const float* wf32, const bf16* wsplit, long long split_plane, const BlockBuffers& b,
+                      int precision, cudaStream_t st) {
+  const int M = cells * tokens;
+  const long long pa = (long long)M * D, ph = (long long)M * 4 * D;
+  for (int l = 0; l < depth; ++l) {
+    const ribca_block_desc& w = blocks[l];
+    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln1_g, wf32 + w.ln1_b, 1e-6f, b.a, pa, st));
+    RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, 3 * D, D, wf32 + w.qkv_b, nullptr, 0,
+                          RIBCA_EPI_STORE, b.qkv, nullptr, 0, precision, st));
+    RIBCA_TRY(attention_launch(b.qkv, cells, tokens, heads, D / heads, b.a, pa, st));
+    RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
+                          RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, st));
+    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, b.a, pa, st));
+    RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.fc1_w, split_plane, M, 4 * D, D, wf32 + w.fc1_b, nullptr, 0,
+                          RIBCA_EPI_GELU, nullptr, b.h, ph, precision, st));
+    RIBCA_TRY(gemm_launch(b.h, ph, wsplit + w.fc2_w, split_plane, M, D, 4 * D, wf32 + w.fc2_b, nullptr, 0,
+                          RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, st));
+  }
+  return RIBCA_OK;
+}
+
+struct Carver {
+  char* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static size_t block_buffers(Carver& cv, BlockBuffers& b, long long M, int D) {
+  b.x = cv.take<float>(M * D);
+  b.a = cv.take<bf16>(2 * M * D);
+  b.qkv = cv.take<float>(M * 3 * D);
+  b.h = cv.take<bf16>(2 * M * 4 * D);
+  return cv.off;
+}
+
+}  // namespace ribca
+
+using namespace ribca;
+
+extern "C" {
+
+int ribca_layernorm_split(const float* x, int M, int D, const float* gamma, const float* beta, float eps,
+                          void* out_split, long long out_plane, ribca_stream_t stream) {
+  RIBCA_REQUIRE(x && gamma && beta && out_split, "ribca_layernorm_split: null pointer");
+  return layernorm_launch(x, M, D, gamma, beta, eps, out_split, out_plane, as_stream(stream));
+}
+
+int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head_dim, void* out_split,
+                    long long out_plane, ribca_stream_t stream) {
+  RIBCA_REQUIRE(qkv && out_split && heads > 0, "ribca_attention: bad arguments");
+  return attention_launch(qkv, cells, tokens, heads, head_dim, out_split, out_plane, as_stream(stream));
+}
+
+size_t ribca_vit_workspace_bytes(const ribca_vit_desc* desc, int n_cells) {
+  if (!desc || n_cells <= 0) return 0;
+  Carver cv{nullptr, 0};
+  BlockBuffers b;
+  block_buffers(cv, b, (long long)n_cells * desc->tokens, desc->dim);
+  return align_up(cv.off, 256);
+}
+
+int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void* wsplit_, const float* patches,
+                      int n_cells, float* probs, float* logits, void* workspace, size_t workspace_bytes,
+                      int precision, ribca_stream_t stream) {
+  RIBCA_REQUIRE(desc && wf32 && wsplit_ && patches && probs && workspace, "ribca_vit_forward: null pointer");
+  RIBCA_REQUIRE(desc->tokens == 101 && desc->depth > 0 && desc->depth <= 16 && desc->classes <= 16 && desc->dim <= 768 &&
+                    desc->dim % desc->heads == 0 && desc->in_chans <= RIBCA_MAX_PANEL_CH,
+                "ribca_vit_forward: unsupported model shape");
+  if (n_cells <= 0) return RIBCA_OK;
+  if (workspace_bytes < ribca_vit_workspace_bytes(desc, n_cells)) {
+    set_error("ribca_vit_forward: workspace %zu < %zu", workspace_bytes, ribca_vit_workspace_bytes(desc, n_cells));
+    return RIBCA_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const bf16* wsplit = static_cast<const bf16*>(wsplit_);
+  const int D = desc->dim, T = desc->tokens, C = desc->in_chans;
+  const long long M = (long long)n_cells * T;
+  RIBCA_REQUIRE(M < (1ll << 31) / 16, "ribca_vit_forward: %d cells per call is too many; chunk the batch", n_cells);
+  Carver cv{static_cast<char*>(workspace), 0};
+  BlockBuffers b;
+  block_buffers(cv, b, M, D);
+  // patch embedding: im2col into the (larger) MLP buffer, GEMM with the cls/pos/bias row table
+  const int Kpe = 16 * C;
+  const long long pe_plane = M * Kpe;
+  im2col_split_kernel<<<grid_for((long long)n_cells * C * 400, 256), 256, 0, st>>>(patches, n_cells, C, b.h, b.h + pe_plane);
+  RIBCA_LAUNCH_CHECK("im2col_split_kernel");
+  RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
+                        wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, st));
+  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, st));
+  head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(b.x, n_cells, T, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
+                                                         wf32 + desc->head_w, wf32 + desc->head_b, desc->classes, probs, logits);
+  RIBCA_LAUNCH_CHECK("head_softmax_kernel");
+  return RIBCA_OK;
+}
+
+static void mae_carve(const ribca_mae_desc* d, int n_cells, int n_present, Carver& cv, BlockBuffers& be, BlockBuffers& bd,
+                      float*& emb, float*& pred, float*& table) {
+  const long long Me = (long long)n_cells * (n_present + 1), Md = (long long)n_cells * (d->channels + 1);
+  block_buffers(cv, be, Me, d->enc_dim);
+  block_buffers(cv, bd, Md, d->dec_dim);
+  emb = cv.take<float>(Me * d->dec_dim);
+  pred = cv.take<float>(Md * 1600);
+  table = cv.take<float>((size_t)(n_present + 1) * d->enc_dim);
+}
+
+size_t ribca_mae_workspace_bytes(const ribca_mae_desc* desc, int n_cells) {
+  if (!desc || n_cells <= 0) return 0;
+  Carver cv{nullptr, 0};
+  BlockBuffers be, bd; float *emb, *pred, *table;
+  mae_carve(desc, n_cells, desc->channels, cv, be, bd, emb, pred, table);   // worst case: every marker present
+  return align_up(cv.off, 256);
+}
+
+int ribca_mae_impute(const ribca_mae_desc* desc, const float* wf32, const void* wsplit_, float* patches, int n_cells,
+                     const int* h_present, int n_present, void* workspace, size_t workspace_bytes, int precision,
+                     ribca_stream_t stream) {
+  RIBCA_REQUIRE(desc && wf32 && wsplit_ && patches && h_present && workspace, "ribca_mae_impute: null pointer");
+  const int L = desc->channels;
+  RIBCA_REQUIRE(L > 0 && L <= RIBCA_MAX_PANEL_CH && n_present > 0 && n_present <= L, "ribca_mae_impute: bad channel counts");
+  RIBCA_REQUIRE(desc->enc_depth <= 16 && desc->dec_depth <= 16, "ribca_mae_impute: too many blocks");
+  if (n_cells <= 0 || n_present == L) return RIBCA_OK;
+  if (workspace_bytes < ribca_mae_workspace_bytes(desc, n_cells)) {
+    set_error("ribca_mae_impute: workspace %zu < %zu", workspace_bytes, ribca_mae_workspace_bytes(desc, n_cells));
+    return RIBCA_EWORKSPACE;
+  }
+  PresentList pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.n = n_present;
+  for (int c = 0; c < RIBCA_MAX_PANEL_CH; ++c) pl.rank[c] = -1;
+  for (int i = 0; i < n_present; ++i) {
+    RIBCA_REQUIRE(h_present[i] >= 0 && h_present[i] < L && (i == 0 || h_present[i] > h_present[i - 1]),
+                  "ribca_mae_impute: present list must be ascending positions in [0,%d)", L);
+    pl.idx[i] = h_present[i];
+    pl.rank[h_present[i]] = i;
+  }
+  cudaStream_t st = as_stream(stream);
+  const bf16* wsplit = static_cast<const bf16*>(wsplit_);
+  const int De = desc->enc_dim, Dd = desc->dec_dim, Te = n_present + 1, Td = L + 1;
+  const long long Me = (long long)n_cells * Te, Md = (long long)n_cells * Td;
+  Carver cv{static_cast<char*>(workspace), 0};
+  BlockBuffers be, bd; float *emb, *pred, *table;
+  mae_carve(desc, n_cells, n_present, cv, be, bd, emb, pred, table);
+
+  // encoder (markerImputer.py:186-206)
+  const long long tile_plane = Me * 1600;
+  mae_tiles_split_kernel<<<grid_for(Me * 400, 256), 256, 0, st>>>(patches, n_cells, L, pl, be.h, be.h + tile_plane);
+  RIBCA_LAUNCH_CHECK("mae_tiles_split_kernel");
+  mae_enc_table_kernel<<<grid_for((long long)Te * De, 256), 256, 0, st>>>(wf32 + desc->cls_token, wf32 + desc->embed_bias,
+                                                                         wf32 + desc->pos_embed, De, pl, table);
+  RIBCA_LAUNCH_CHECK("mae_enc_table_kernel");
+  RIBCA_TRY(gemm_launch(be.h, tile_plane, wsplit + desc->embed_w, desc->split_plane, (int)Me, De, 1600, nullptr, table, Te,
+                        RIBCA_EPI_STORE, be.x, nullptr, 0, precision, st));
+  RIBCA_TRY(run_blocks(desc->enc_blocks, desc->enc_depth, De, desc->enc_heads, n_cells, Te, wf32, wsplit, desc->split_plane, be, precision, st));
+  RIBCA_TRY(layernorm_launch(be.x, (int)Me, De, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f, be.a, Me * De, st));
+  // decoder (markerImputer.py:208-232)
+  RIBCA_TRY(gemm_launch(be.a, Me * De, wsplit + desc->dec_embed_w, desc->split_plane, (int)Me, Dd, De, wf32 + desc->dec_embed_b,
+                        nullptr, 0, RIBCA_EPI_STORE, emb, nullptr, 0, precision, st));
+  mae_decoder_input_kernel<<<grid_for(Md * Dd, 256), 256, 0, st>>>(emb, wf32 + desc->mask_token, wf32 + desc->dec_pos_embed,
+                                                                    n_cells, L, Dd, pl, bd.x);
+  RIBCA_LAUNCH_CHECK("mae_decoder_input_kernel");
+  RIBCA_TRY(run_blocks(desc->dec_blocks, desc->dec_depth, Dd, desc->dec_heads, n_cells, Td, wf32, wsplit, desc->split_plane, bd, precision, st));
+  RIBCA_TRY(layernorm_launch(bd.x, (int)Md, Dd, wf32 + desc->dec_norm_g, wf32 + desc->dec_norm_b, 1e-6f, bd.a, Md * Dd, st));
+  RIBCA_TRY(gemm_launch(bd.a, Md * Dd, wsplit + desc->pred_w, desc->split_plane, (int)Md, 1600, Dd, wf32 + desc->pred_b, nullptr, 0,
+                        RIBCA_EPI_STORE, pred, nullptr, 0, precision, st));
+  mae_scatter_kernel<<<grid_for((long long)n_cells * L * 400, 256), 256, 0, st>>>(pred, n_cells, L, pl, patches);
+  RIBCA_LAUNCH_CHECK("mae_scatter_kernel");
+  return RIBCA_OK;
+}
+
+}  // extern "C"

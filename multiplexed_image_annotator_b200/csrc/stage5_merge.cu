@@ -1,0 +1,126 @@
+// Stage 5: vote merge, "Others" threshold and per-type counts in one pass over the softmax tables.
+// Replaces Annotator.merge_by_voting + get_void_vote (reference cta/model.py:481-636,
+// cta/utils.py:143-146).  All comparisons are float32 (numpy >= 2 rounds the Python-float
+// thresholds to float32 before comparing with the np.float32 votes).
+//
+//   one model : best = first argmax in class order (incl. "Others"); thr = ctc[best] > 0 ? ctc[best]
+//               : confidence; best != Others and p < thr -> ("Others", -1) else (best, p)
+//   two models: vote[type] = the probability of the (single) model that predicts that type, 0 for
+//               types no model predicts; best = first maximum in get_void_vote() key order;
+//               thr = ctc[best] < 0 ? min(others_0, others_1, confidence) : ctc[best];
+//               vote < thr -> ("Others", -1) else (best, vote)
+// HBM-bound: 4 * (classes0 + classes1) bytes read and 5 bytes written per cell.
+#include "common.cuh"
+
+namespace ribca {
+
+constexpr int kTypes = 18;
+constexpr int kOthers = 17;
+constexpr int kMaxClasses = 16;
+
+struct MergeParams {
+  int classes[2];
+  int type_of_class[2][kMaxClasses];
+  int order[kTypes];          // order[i] = global type at position i of the vote key order (17 entries)
+  float type_thresh[kTypes];
+  float confidence;
+};
+
+__global__ void __launch_bounds__(256)
+merge_votes_kernel(const float* __restrict__ p0, const float* __restrict__ p1, int n,
+                   const __grid_constant__ MergeParams prm, uint8_t* __restrict__ label,
+                   float* __restrict__ conf, long long* __restrict__ counts) {
+  __shared__ int hist[kTypes];
+  if (threadIdx.x < kTypes) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int best;
+    float value;
+    if (p1 == nullptr) {
+      const float* row = p0 + (long long)i * prm.classes[0];
+      int k = 0;
+      float pk = row[0];
+      for (int c = 1; c < prm.classes[0]; ++c) {
+        const float v = row[c];
+        if (v > pk) { pk = v; k = c; }
+      }
+      best = prm.type_of_class[0][k];
+      const float t = prm.type_thresh[best];
+      const float thr = t > 0.0f ? t : prm.confidence;
+      value = pk;
+      if (best != kOthers && pk < thr) { best = kOthers; value = -1.0f; }
+    } else {
+      float vote[kTypes];
+#pragma unroll
+      for (int t = 0; t < kTypes; ++t) vote[t] = 0.0f;
+      float others[2] = {0.0f, 0.0f};
+      const float* rows[2] = {p0 + (long long)i * prm.classes[0], p1 + (long long)i * prm.classes[1]};
+      for (int m = 0; m < 2; ++m)
+        for (int c = 0; c < prm.classes[m]; ++c) {
+          const int t = prm.type_of_class[m][c];
+          const float v = rows[m][c];
+          if (t == kOthers) others[m] = v;
+          else vote[t] = __fadd_rn(vote[t], v);
+        }
+      best = prm.order[0];
+      float bv = vote[best];
+      for (int q = 1; q < kTypes - 1; ++q) {
+        const int t = prm.order[q];
+        if (vote[t] > bv) { bv = vote[t]; best = t; }
+      }
+      const float t = prm.type_thresh[best];
+      // Python min(o1, o2, confidence): first minimal element, float32 comparisons
+      float thr = others[0];
+      if (others[1] < thr) thr = others[1];
+      if (prm.confidence < thr) thr = prm.confidence;
+      if (!(t < 0.0f)) thr = t;
+      value = bv;
+      if (bv < thr) { best = kOthers; value = -1.0f; }
+    }
+    label[i] = (uint8_t)best;
+    conf[i] = value;
+    atomicAdd(&hist[best], 1);
+  }
+  __syncthreads();
+  if (counts && threadIdx.x < kTypes && hist[threadIdx.x])
+    atomicAdd(reinterpret_cast<unsigned long long*>(counts) + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
+}
+
+}  // namespace ribca
+
+using namespace ribca;
+
+extern "C" int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_class0,
+                                 const float* probs1, int classes1, const int* h_type_of_class1, int n_cells,
+                                 const int* h_vote_rank, const float* h_type_thresh, float confidence,
+                                 uint8_t* label, float* conf, long long* counts, ribca_stream_t stream) {
+  RIBCA_REQUIRE(probs0 && h_type_of_class0 && h_vote_rank && h_type_thresh && label && conf,
+                "ribca_merge_votes: null pointer");
+  RIBCA_REQUIRE(classes0 > 0 && classes0 <= kMaxClasses, "ribca_merge_votes: classes0=%d", classes0);
+  RIBCA_REQUIRE(!probs1 || (classes1 > 0 && classes1 <= kMaxClasses && h_type_of_class1), "ribca_merge_votes: bad second model");
+  if (n_cells <= 0) return RIBCA_OK;
+  MergeParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.classes[0] = classes0;
+  prm.classes[1] = probs1 ? classes1 : 0;
+  for (int c = 0; c < classes0; ++c) {
+    RIBCA_REQUIRE(h_type_of_class0[c] >= 0 && h_type_of_class0[c] < kTypes, "ribca_merge_votes: bad type index");
+    prm.type_of_class[0][c] = h_type_of_class0[c];
+  }
+  for (int c = 0; c < prm.classes[1]; ++c) {
+    RIBCA_REQUIRE(h_type_of_class1[c] >= 0 && h_type_of_class1[c] < kTypes, "ribca_merge_votes: bad type index");
+    prm.type_of_class[1][c] = h_type_of_class1[c];
+  }
+  for (int t = 0; t < kTypes; ++t) prm.order[t] = kOthers;
+  for (int t = 0; t < kTypes - 1; ++t) {
+    const int rank = h_vote_rank[t];
+    RIBCA_REQUIRE(rank >= 0 && rank < kTypes - 1, "ribca_merge_votes: vote rank %d of type %d out of range", rank, t);
+    prm.order[rank] = t;
+  }
+  for (int t = 0; t < kTypes; ++t) prm.type_thresh[t] = h_type_thresh[t];
+  prm.confidence = confidence;
+  merge_votes_kernel<<<(n_cells + 255) / 256, 256, 0, as_stream(stream)>>>(probs0, probs1, n_cells, prm, label, conf, counts);
+  RIBCA_LAUNCH_CHECK("merge_votes_kernel");
+  return RIBCA_OK;
+}

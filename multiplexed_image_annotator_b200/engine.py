@@ -1,0 +1,187 @@
+"""Device-resident classifier / imputer engines over ribca_vit_forward and ribca_mae_impute.
+
+A timm-format state dict (reference checkpoint layout, model.py:191, markerImputer.py:261,285) is
+packed once into two device blobs - fp32 parameters and split-bf16 GEMM weights {hi, lo} - plus a
+C descriptor of element offsets (include/ribca_b200.h: ribca_vit_desc / ribca_mae_desc).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .weights import MAE_SPECS, VIT_SPECS, MaeSpec, VitSpec
+
+
+class _Packer:
+    def __init__(self):
+        self.f32, self.f32_off = [], 0
+        self.mat, self.mat_off = [], 0
+
+    @staticmethod
+    def _pad(t, mult=64):
+        n = t.numel()
+        pad = (-n) % mult
+        flat = t.reshape(-1).to(torch.float32)
+        return torch.cat([flat, flat.new_zeros(pad)]) if pad else flat
+
+    def add_f32(self, t) -> int:
+        off = self.f32_off
+        p = self._pad(t)
+        self.f32.append(p)
+        self.f32_off += p.numel()
+        return off
+
+    def add_mat(self, t) -> int:
+        off = self.mat_off
+        p = self._pad(t)
+        self.mat.append(p)
+        self.mat_off += p.numel()
+        return off
+
+    def finish(self, device):
+        wf32 = torch.cat(self.f32).to(device)
+        mats = torch.cat(self.mat).to(device)
+        wsplit = ops.split_bf16(mats)                 # (2, total) bf16, plane stride = total
+        return wf32, wsplit, self.mat_off
+
+
+def _pack_block(pk: _Packer, sd, prefix: str, desc: _lib.BlockDesc):
+    desc.ln1_g = pk.add_f32(sd[f"{prefix}.norm1.weight"]); desc.ln1_b = pk.add_f32(sd[f"{prefix}.norm1.bias"])
+    desc.ln2_g = pk.add_f32(sd[f"{prefix}.norm2.weight"]); desc.ln2_b = pk.add_f32(sd[f"{prefix}.norm2.bias"])
+    desc.qkv_b = pk.add_f32(sd[f"{prefix}.attn.qkv.bias"]); desc.proj_b = pk.add_f32(sd[f"{prefix}.attn.proj.bias"])
+    desc.fc1_b = pk.add_f32(sd[f"{prefix}.mlp.fc1.bias"]); desc.fc2_b = pk.add_f32(sd[f"{prefix}.mlp.fc2.bias"])
+    desc.qkv_w = pk.add_mat(sd[f"{prefix}.attn.qkv.weight"]); desc.proj_w = pk.add_mat(sd[f"{prefix}.attn.proj.weight"])
+    desc.fc1_w = pk.add_mat(sd[f"{prefix}.mlp.fc1.weight"]); desc.fc2_w = pk.add_mat(sd[f"{prefix}.mlp.fc2.weight"])
+
+
+class _Workspace:
+    """Grow-only device scratch shared by the engines of one process."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_WS = _Workspace()
+
+
+class VitEngine:
+    """One panel's ViT classifier (reference model.py:31-88) resident on a CUDA device."""
+
+    def __init__(self, spec: VitSpec | str, state_dict: dict, device="cuda", precision: str = "bf16x3",
+                 max_cells_per_call: int = 4096):
+        self.spec = VIT_SPECS[spec] if isinstance(spec, str) else spec
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("VitEngine needs a CUDA device: the B200 path has no CPU fallback")
+        self.precision = precision
+        self.max_cells = max_cells_per_call
+        s = self.spec
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()}
+        want = (1, s.tokens, s.dim)
+        if tuple(sd["pos_embed"].shape) != want:
+            raise ValueError(f"pos_embed {tuple(sd['pos_embed'].shape)} does not match {want}")
+        pk = _Packer()
+        d = _lib.VitDesc()
+        d.dim, d.heads, d.depth, d.in_chans, d.classes, d.tokens = s.dim, s.heads, s.depth, s.in_chans, len(s.classes), s.tokens
+        pos = sd["pos_embed"][0]
+        table = pos + sd["patch_embed.proj.bias"][None, :]
+        table[0] = pos[0] + sd["cls_token"].reshape(-1)
+        d.embed_table = pk.add_f32(table)
+        d.embed_w = pk.add_mat(sd["patch_embed.proj.weight"].reshape(s.dim, -1))
+        d.norm_g = pk.add_f32(sd["norm.weight"]); d.norm_b = pk.add_f32(sd["norm.bias"])
+        d.head_w = pk.add_f32(sd["head.weight"]); d.head_b = pk.add_f32(sd["head.bias"])
+        for i in range(s.depth):
+            _pack_block(pk, sd, f"blocks.{i}", d.blocks[i])
+        self.wf32, self.wsplit, d.split_plane = pk.finish(self.device)
+        self.desc = d
+
+    def set_head(self, weight: torch.Tensor, bias: torch.Tensor):
+        """Replace the classification head in place (used by the calibration recipe)."""
+        k, dim = len(self.spec.classes), self.spec.dim
+        self.wf32[self.desc.head_w: self.desc.head_w + k * dim] = weight.reshape(-1).to(self.device, torch.float32)
+        self.wf32[self.desc.head_b: self.desc.head_b + k] = bias.reshape(-1).to(self.device, torch.float32)
+
+    @torch.no_grad()
+    def forward(self, patches: torch.Tensor, return_logits: bool = False, precision: str | None = None):
+        """patches (n, C, 40, 40) float32 on the device -> softmax probabilities (n, classes)."""
+        ops._need_cuda(patches)
+        n, c = patches.shape[0], patches.shape[1]
+        if c != self.spec.in_chans or patches.shape[2:] != (40, 40) or patches.dtype != torch.float32:
+            raise ValueError(f"expected (n, {self.spec.in_chans}, 40, 40) float32 patches, got {tuple(patches.shape)} {patches.dtype}")
+        L = _lib.lib()
+        k = len(self.spec.classes)
+        probs = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        logits = torch.empty((n, k), dtype=torch.float32, device=self.device) if return_logits else None
+        prec = ops.PRECISION[precision or self.precision]
+        for i in range(0, n, self.max_cells):
+            m = min(self.max_cells, n - i)
+            ws_bytes = L.ribca_vit_workspace_bytes(C.byref(self.desc), m)
+            ws = _WS.get(ws_bytes, self.device)
+            _lib.check(L.ribca_vit_forward(C.byref(self.desc), ops._ptr(self.wf32), ops._ptr(self.wsplit),
+                                           ops._ptr(patches[i:i + m]), m, ops._ptr(probs[i:i + m]),
+                                           ops._ptr(logits[i:i + m]) if logits is not None else 0,
+                                           ops._ptr(ws), ws.numel(), prec, ops._stream()), "ribca_vit_forward")
+        return (probs, logits) if return_logits else probs
+
+
+class MaeEngine:
+    """One panel's MAE marker imputer (reference markerImputer.py:69-329) resident on a CUDA device."""
+
+    def __init__(self, spec: MaeSpec | str, state_dict: dict, device="cuda", precision: str = "bf16x3",
+                 max_cells_per_call: int = 2048):
+        self.spec = MAE_SPECS[spec] if isinstance(spec, str) else spec
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("MaeEngine needs a CUDA device: the B200 path has no CPU fallback")
+        self.precision = precision
+        self.max_cells = max_cells_per_call
+        s = self.spec
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()}
+        pk = _Packer()
+        d = _lib.MaeDesc()
+        d.channels = s.channels
+        d.enc_dim, d.enc_heads, d.enc_depth = s.enc_dim, s.enc_heads, s.enc_depth
+        d.dec_dim, d.dec_heads, d.dec_depth = s.dec_dim, s.dec_heads, s.dec_depth
+        d.embed_w = pk.add_mat(sd["patch_embed.proj.weight"].reshape(s.enc_dim, 1600))
+        d.embed_bias = pk.add_f32(sd["patch_embed.proj.bias"])
+        d.cls_token = pk.add_f32(sd["cls_token"]); d.pos_embed = pk.add_f32(sd["pos_embed"])
+        d.norm_g = pk.add_f32(sd["norm.weight"]); d.norm_b = pk.add_f32(sd["norm.bias"])
+        d.dec_embed_w = pk.add_mat(sd["decoder_embed.weight"]); d.dec_embed_b = pk.add_f32(sd["decoder_embed.bias"])
+        d.mask_token = pk.add_f32(sd["mask_token"]); d.dec_pos_embed = pk.add_f32(sd["decoder_pos_embed"])
+        d.dec_norm_g = pk.add_f32(sd["decoder_norm.weight"]); d.dec_norm_b = pk.add_f32(sd["decoder_norm.bias"])
+        d.pred_w = pk.add_mat(sd["decoder_pred.weight"]); d.pred_b = pk.add_f32(sd["decoder_pred.bias"])
+        for i in range(s.enc_depth):
+            _pack_block(pk, sd, f"blocks.{i}", d.enc_blocks[i])
+        for i in range(s.dec_depth):
+            _pack_block(pk, sd, f"decoder_blocks.{i}", d.dec_blocks[i])
+        self.wf32, self.wsplit, d.split_plane = pk.finish(self.device)
+        self.desc = d
+
+    @torch.no_grad()
+    def impute(self, patches: torch.Tensor, present, precision: str | None = None) -> torch.Tensor:
+        """In place: channels not listed in `present` (ascending panel positions) are replaced by the
+        decoder's prediction; present channels are left untouched.  Returns `patches`."""
+        ops._need_cuda(patches)
+        n, c = patches.shape[0], patches.shape[1]
+        if c != self.spec.channels or patches.dtype != torch.float32:
+            raise ValueError(f"expected (n, {self.spec.channels}, 40, 40) float32 patches")
+        present = sorted(int(p) for p in present)
+        L = _lib.lib()
+        arr = (C.c_int * len(present))(*present)
+        prec = ops.PRECISION[precision or self.precision]
+        for i in range(0, n, self.max_cells):
+            m = min(self.max_cells, n - i)
+            ws_bytes = L.ribca_mae_workspace_bytes(C.byref(self.desc), m)
+            ws = _WS.get(ws_bytes, self.device)
+            _lib.check(L.ribca_mae_impute(C.byref(self.desc), ops._ptr(self.wf32), ops._ptr(self.wsplit),
+                                          ops._ptr(patches[i:i + m]), m, arr, len(present), ops._ptr(ws), ws.numel(),
+                                          prec, ops._stream()), "ribca_mae_impute")
+        return patches

@@ -1,0 +1,287 @@
+"""Typed Python wrappers over the C ABI (include/ribca_b200.h).
+
+PyTorch is used here only to own device memory and streams; every computation is a call into
+libribca_b200.so with raw device pointers.  The small host-side plans (Gaussian tap weights,
+np.percentile order statistics) are computed with the same numpy expressions scipy / numpy use,
+which is what makes the device results bit-identical to the reference's CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PATCH = 40
+MAX_PANEL_CH = 16
+GAUSS_STRIDE = 16
+PRECISION = {"bf16x3": 0, "bf16": 1, "bf16x1": 1, "simt": 2, "fp32": 2}
+EPI_STORE, EPI_RESIDUAL, EPI_GELU = 0, 1, 2
+_DTYPES = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2, torch.int32: 3}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+            raise RuntimeError("libribca_b200 operates on contiguous CUDA tensors only (no CPU fallback)")
+
+
+def launch_count() -> int:
+    return int(_lib.lib().ribca_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side plans
+# ------------------------------------------------------------------------------------------------
+def gaussian_half_kernel(sigma, truncate: float = 4.0):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius) from the centre outwards:
+    returns (w[0..r], r) with r = int(truncate * sigma + 0.5)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / sigma2 * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[::-1][radius:], dtype=np.float64), radius
+
+
+def percentile_plan(n: int, amax, dtype=np.float32):
+    """(k_lo, k_hi, gamma) of np.percentile(x, amax) for a float32 array of n elements, method
+    'linear' (numpy/lib/_function_base_impl.py: percentile -> _quantile -> _get_indexes/_get_gamma).
+    The quantile and the virtual index are float32 because numpy divides by `a.dtype.type(100)`."""
+    q = np.asanyarray(np.true_divide(amax, dtype(100)))
+    vi = np.asanyarray((n - 1) * q)
+    prev = np.asanyarray(np.floor(vi))
+    nxt = np.asanyarray(prev + 1)
+    if vi >= n - 1:
+        prev = nxt = np.asanyarray(-1.0)
+    if vi < 0:
+        prev = nxt = np.asanyarray(0.0)
+    prev_i, nxt_i = prev.astype(np.intp), nxt.astype(np.intp)
+    gamma = np.asanyarray(vi - prev_i, dtype=vi.dtype)
+    k_lo, k_hi = int(prev_i), int(nxt_i)
+    if k_lo < 0:
+        k_lo += n
+    if k_hi < 0:
+        k_hi += n
+    return k_lo, k_hi, float(gamma)
+
+
+def _dptr(arr: np.ndarray):
+    return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 1
+# ------------------------------------------------------------------------------------------------
+def normalize(img: torch.Tensor, blur=0.3, amax=99.8, return_stats: bool = False):
+    """ImageProcessor._normalize on the device.  img: (C, H, W) uint8 / uint16 / int32 / float32."""
+    _need_cuda(img)
+    if img.dtype not in _DTYPES:
+        raise TypeError(f"unsupported image dtype {img.dtype}")
+    c, h, w = img.shape
+    L = _lib.lib()
+    w_bg, r_bg = gaussian_half_kernel(20)
+    if blur:
+        w_bl, r_bl = gaussian_half_kernel(blur)
+    else:
+        w_bl, r_bl = np.zeros(1), -1
+    k_lo, k_hi, gamma = percentile_plan(h * w, amax)
+    out = torch.empty((c, h, w), dtype=torch.float32, device=img.device)
+    stats = torch.empty((c, 4), dtype=torch.float32, device=img.device)
+    ws_bytes = L.ribca_normalize_workspace_bytes(c, h, w)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+    _lib.check(L.ribca_normalize(_ptr(img), _DTYPES[img.dtype], c, h, w, _dptr(w_bg), r_bg, _dptr(w_bl), r_bl,
+                                 k_lo, k_hi, gamma, _ptr(out), _ptr(stats), _ptr(ws), ws_bytes, _stream()),
+               "ribca_normalize")
+    return (out, stats) if return_stats else out
+
+
+def channel_min(img: torch.Tensor) -> torch.Tensor:
+    _need_cuda(img)
+    c = img.shape[0]
+    out = torch.empty(c, dtype=torch.float32, device=img.device)
+    _lib.check(_lib.lib().ribca_channel_min(_ptr(img), c, img[0].numel(), _ptr(out), _stream()), "ribca_channel_min")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 2
+# ------------------------------------------------------------------------------------------------
+class CellTable:
+    """Compacted per-cell statistics on the device (ids ascending)."""
+
+    def __init__(self, ids, bbox, sums, count, id_to_index, n, max_id):
+        self.ids, self.bbox, self.sums, self.count = ids, bbox, sums, count
+        self.id_to_index, self.n, self.max_id = id_to_index, n, max_id
+
+    def centroids(self) -> torch.Tensor:
+        """np.mean of the pixel lists: exact integer sums, one float64 division (model.py:785-786)."""
+        return self.sums.to(torch.float64) / self.count.to(torch.float64).unsqueeze(1)
+
+
+def cell_stats(mask: torch.Tensor) -> CellTable:
+    """_cell_pos_dict reduced to (ids, bbox, coordinate sums, area).  mask: (H, W) int32 on the device."""
+    _need_cuda(mask)
+    if mask.dtype != torch.int32 or mask.dim() != 2:
+        raise TypeError("mask must be a 2-D int32 tensor")
+    L = _lib.lib()
+    h, w = mask.shape
+    dev = mask.device
+    mm = torch.empty(2, dtype=torch.int32, device=dev)
+    _lib.check(L.ribca_mask_minmax(_ptr(mask), mask.numel(), _ptr(mm), _stream()), "ribca_mask_minmax")
+    lo, hi = (int(v) for v in mm.tolist())         # the one host sync of stage 2: table sizes depend on it
+    if lo < 0:
+        raise ValueError("negative cell labels are not supported")
+    if hi > (1 << 27):
+        raise ValueError(f"largest label {hi} exceeds the dense-table limit 2^27; relabel the mask")
+    n_ids = hi + 1
+    bbox = torch.empty((n_ids, 4), dtype=torch.int32, device=dev)
+    sums = torch.empty((n_ids, 2), dtype=torch.int64, device=dev)
+    count = torch.empty(n_ids, dtype=torch.int32, device=dev)
+    _lib.check(L.ribca_cell_stats(_ptr(mask), h, w, hi, _ptr(bbox), _ptr(sums), _ptr(count), _stream()), "ribca_cell_stats")
+    ids = torch.empty(n_ids, dtype=torch.int32, device=dev)
+    cbbox = torch.empty((n_ids, 4), dtype=torch.int32, device=dev)
+    csums = torch.empty((n_ids, 2), dtype=torch.int64, device=dev)
+    ccount = torch.empty(n_ids, dtype=torch.int32, device=dev)
+    id2idx = torch.empty(n_ids, dtype=torch.int32, device=dev)
+    n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = L.ribca_compact_workspace_bytes(hi)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(L.ribca_compact_cells(_ptr(bbox), _ptr(sums), _ptr(count), hi, _ptr(ids), _ptr(cbbox), _ptr(csums),
+                                     _ptr(ccount), _ptr(id2idx), _ptr(n_dev), _ptr(ws), ws_bytes, _stream()),
+               "ribca_compact_cells")
+    n = int(n_dev.item())
+    return CellTable(ids[:n], cbbox[:n], csums[:n], ccount[:n], id2idx, n, hi)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 3
+# ------------------------------------------------------------------------------------------------
+_GAUSS = None
+
+
+def _gauss_table() -> np.ndarray:
+    global _GAUSS
+    if _GAUSS is None:
+        tab = np.zeros((3, GAUSS_STRIDE), dtype=np.float64)
+        for s in (1, 2, 3):
+            wts, r = gaussian_half_kernel(s)
+            tab[s - 1, : r + 1] = wts
+        _GAUSS = tab
+    return _GAUSS
+
+
+def build_patches(img: torch.Tensor, mask: torch.Tensor, min_val: torch.Tensor, cells: CellTable, panels,
+                  cell_begin: int = 0, n_cells: int | None = None, want_intensity: bool = False,
+                  want_windows: bool = False):
+    """crop_cell + smooth + channel select for cells [cell_begin, cell_begin + n_cells).
+    panels: list of channel-index lists (may contain -1).  Returns (list of (n, C_p, 40, 40) float32
+    tensors, avg_int (n, C_img) float64 or None, windows (n, 4) int32 or None)."""
+    _need_cuda(img, mask, min_val)
+    L = _lib.lib()
+    c_img, h, w = img.shape
+    n = cells.n - cell_begin if n_cells is None else n_cells
+    dev = img.device
+    npan = len(panels)
+    if npan > 3:
+        raise ValueError("at most 3 panels per call")
+    n_ch = (C.c_int * max(npan, 1))(*[len(p) for p in panels])
+    idx = (C.c_int * (max(npan, 1) * MAX_PANEL_CH))()
+    outs = []
+    out_ptrs = (C.c_void_p * max(npan, 1))()
+    for p, chans in enumerate(panels):
+        if len(chans) > MAX_PANEL_CH:
+            raise ValueError("panel too wide")
+        for k, ch in enumerate(chans):
+            idx[p * MAX_PANEL_CH + k] = int(ch)
+        t = torch.empty((n, len(chans), PATCH, PATCH), dtype=torch.float32, device=dev)
+        outs.append(t)
+        out_ptrs[p] = t.data_ptr()
+    avg = torch.empty((n, c_img), dtype=torch.float64, device=dev) if want_intensity else None
+    wins = torch.empty((n, 4), dtype=torch.int32, device=dev) if want_windows else None
+    g = _gauss_table()
+    _lib.check(L.ribca_build_patches(_ptr(img), _ptr(mask), c_img, h, w, _ptr(min_val), _ptr(cells.ids), _ptr(cells.bbox),
+                                     cell_begin, n, npan, n_ch, idx, out_ptrs, _dptr(g), _ptr(avg), _ptr(wins), _stream()),
+               "ribca_build_patches")
+    return outs, avg, wins
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 4 primitives
+# ------------------------------------------------------------------------------------------------
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor -> (2, *shape) bf16 planes {hi, lo} with x ~= hi + lo."""
+    _need_cuda(x)
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().ribca_split_bf16(_ptr(x), x.numel(), _ptr(out[0]), _ptr(out[1]), _stream()), "ribca_split_bf16")
+    return out
+
+
+def gemm(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None, epilogue=EPI_STORE,
+         out=None, precision="bf16x3"):
+    """out (+)= A . W^T with A (2, M, K), W (2, N, K) split-bf16; see ribca_gemm_splitbf16."""
+    _need_cuda(a_split, w_split, bias, row_table, out)
+    _, m, k = a_split.shape
+    _, n, k2 = w_split.shape
+    assert k == k2
+    dev = a_split.device
+    out_f32 = out_split = None
+    if epilogue == EPI_GELU:
+        out_split = out if out is not None else torch.empty((2, m, n), dtype=torch.bfloat16, device=dev)
+    else:
+        out_f32 = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=dev)
+    period = row_table.shape[0] if row_table is not None else 0
+    _lib.check(_lib.lib().ribca_gemm_splitbf16(_ptr(a_split), m * k, _ptr(w_split), n * k, m, n, k, _ptr(bias), _ptr(row_table),
+                                               period, epilogue, _ptr(out_f32), _ptr(out_split), m * n, PRECISION[precision],
+                                               _stream()), "ribca_gemm_splitbf16")
+    return out_split if epilogue == EPI_GELU else out_f32
+
+
+def layernorm_split(x: torch.Tensor, gamma, beta, eps=1e-6) -> torch.Tensor:
+    _need_cuda(x, gamma, beta)
+    m, d = x.shape
+    out = torch.empty((2, m, d), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().ribca_layernorm_split(_ptr(x), m, d, _ptr(gamma), _ptr(beta), eps, _ptr(out), m * d, _stream()),
+               "ribca_layernorm_split")
+    return out
+
+
+def attention(qkv: torch.Tensor, cells: int, tokens: int, heads: int) -> torch.Tensor:
+    _need_cuda(qkv)
+    m, d3 = qkv.shape
+    d = d3 // 3
+    out = torch.empty((2, m, d), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.lib().ribca_attention(_ptr(qkv), cells, tokens, heads, d // heads, _ptr(out), m * d, _stream()),
+               "ribca_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 5
+# ------------------------------------------------------------------------------------------------
+def merge_votes(probs0, types0, probs1, types1, vote_rank, type_thresh, confidence):
+    """Returns (label uint8 (n,), conf float32 (n,), counts int64 (18,))."""
+    _need_cuda(probs0, probs1)
+    n, k0 = probs0.shape
+    dev = probs0.device
+    label = torch.empty(n, dtype=torch.uint8, device=dev)
+    conf = torch.empty(n, dtype=torch.float32, device=dev)
+    counts = torch.zeros(18, dtype=torch.int64, device=dev)
+    t0 = (C.c_int * len(types0))(*types0)
+    k1 = 0 if probs1 is None else probs1.shape[1]
+    t1 = (C.c_int * max(k1, 1))(*(types1 or [0]))
+    vr = (C.c_int * 18)(*vote_rank)
+    tt = (C.c_float * 18)(*type_thresh)
+    _lib.check(_lib.lib().ribca_merge_votes(_ptr(probs0), k0, t0, _ptr(probs1), k1, t1, n, vr, tt, float(confidence),
+                                            _ptr(label), _ptr(conf), _ptr(counts), _stream()), "ribca_merge_votes")
+    return label, conf, counts

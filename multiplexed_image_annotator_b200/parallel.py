@@ -1,0 +1,47 @@
+"""Multi-GPU partitioning: one process per GPU (torch.distributed), cells sharded by contiguous
+index range, a single gather of per-cell results at the end.  The reference has no
+distributed code; every rank here holds the whole image and mask and redundantly runs stages 1-2,
+then owns cells [lo, hi) for stages 3-5.  Collectives: all_gather of (label, confidence) and
+all_reduce of the 18 per-type counts - NCCL on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, nranks: int):
+    """Contiguous, balanced split of n items: the first n % nranks ranks get one extra."""
+    base, rem = divmod(n, nranks)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, lo: int, hi: int) -> torch.Tensor:
+    """Concatenate every rank's rows [lo, hi) into the full (n_total, ...) tensor on every rank."""
+    rank, nranks = world()
+    if nranks == 1:
+        return local
+    assert local.shape[0] == hi - lo
+    longest = (n_total + nranks - 1) // nranks
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: hi - lo] = local
+    parts = [torch.empty_like(pad) for _ in range(nranks)]
+    dist.all_gather(parts, pad)
+    out = []
+    for r, p in enumerate(parts):
+        a, b = shard_range(n_total, r, nranks)
+        out.append(p[: b - a])
+    return torch.cat(out)
+
+
+def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t

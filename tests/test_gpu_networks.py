@@ -1,0 +1,233 @@
+"""GPU parity tests for stage 4 (tcgen05 split-bf16 GEMM, LayerNorm, attention, ViT, MAE) and the
+end-to-end Annotator, against torch fp32/fp64 references of the same op, the CPU oracle, and the
+reference-generated golden fixtures.
+
+Tolerances (north_star): float probabilities within 1e-3 absolute of the reference; labels exact.
+The bf16x3 GEMM itself is held to a much tighter bound: |err| <= 2e-5 * sum_k |a||w| (dropped lo*lo
+terms + fp32 accumulation); LayerNorm / attention outputs to 2e-6 relative of their split-bf16 range."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ribca_oracle as orc                                  # checker only
+from multiplexed_image_annotator_b200 import engine, ops, synth, weights
+from multiplexed_image_annotator_b200.cell_type_annotation import model as bmodel
+from multiplexed_image_annotator_b200.cell_type_annotation import markerImputer as bimputer
+
+DEV = "cuda"
+
+
+def _unsplit(t):
+    return t[0].double() + t[1].double()
+
+
+def _gemm_case(m, n, k, precision, epilogue=ops.EPI_STORE, bias=True, table_period=0, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    a = torch.randn((m, k), generator=g, device=DEV)
+    w = torch.randn((n, k), generator=g, device=DEV) * 0.05
+    b = torch.randn(n, generator=g, device=DEV) if bias else None
+    tab = torch.randn((table_period, n), generator=g, device=DEV) if table_period else None
+    a_s, w_s = ops.split_bf16(a), ops.split_bf16(w)
+    ref = _unsplit(a_s) @ _unsplit(w_s).T
+    bound = (_unsplit(a_s).abs() @ _unsplit(w_s).abs().T)
+    if b is not None:
+        ref = ref + b.double()
+    if tab is not None:
+        ref = ref + tab.double()[torch.arange(m, device=DEV) % table_period]
+    out0 = None
+    if epilogue == ops.EPI_RESIDUAL:
+        out0 = torch.randn((m, n), generator=g, device=DEV)
+        ref = ref + out0.double()
+        out = ops.gemm(a_s, w_s, b, tab, epilogue, out=out0.clone(), precision=precision)
+        got = out.double()
+    elif epilogue == ops.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+        got = _unsplit(ops.gemm(a_s, w_s, b, tab, epilogue, precision=precision))
+    else:
+        got = ops.gemm(a_s, w_s, b, tab, epilogue, precision=precision).double()
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    rel = (err / bound.clamp_min(1e-6)).max().item()
+    return err.max().item(), rel, ref.abs().max().item()
+
+
+GEMM_SHAPES = [(128, 192, 64), (128, 16, 48), (256, 576, 576), (101 * 5, 1728, 576), (1000, 288, 144), (303, 1600, 512),
+               (77, 2304, 576), (4096, 576, 2304), (640, 768, 1600), (129, 144, 112)]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_simt_matches_fp64(m, n, k):
+    err, rel, mag = _gemm_case(m, n, k, "simt")
+    print(f"simt  M={m} N={n} K={k}: max|err|={err:.3e} rel-to-bound={rel:.3e} |ref|max={mag:.2f}")
+    assert rel < 2e-6
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_tcgen05_bf16x3(m, n, k):
+    err, rel, mag = _gemm_case(m, n, k, "bf16x3")
+    print(f"bf16x3 M={m} N={n} K={k}: max|err|={err:.3e} rel-to-bound={rel:.3e} |ref|max={mag:.2f}")
+    assert rel < 2e-5
+
+
+@pytest.mark.parametrize("epilogue,period", [(ops.EPI_RESIDUAL, 0), (ops.EPI_GELU, 0), (ops.EPI_STORE, 101)])
+def test_gemm_tcgen05_epilogues(epilogue, period):
+    err, rel, mag = _gemm_case(101 * 7, 576, 288, "bf16x3", epilogue, True, period, seed=3)
+    print(f"epilogue {epilogue} period {period}: max|err|={err:.3e} rel={rel:.3e}")
+    assert rel < 3e-5
+
+
+def test_gemm_tcgen05_bf16x1_is_single_pass():
+    err3, rel3, _ = _gemm_case(512, 576, 576, "bf16x3", seed=5)
+    err1, rel1, _ = _gemm_case(512, 576, 576, "bf16x1", seed=5)
+    print(f"bf16x1 rel={rel1:.3e} vs bf16x3 rel={rel3:.3e}")
+    assert rel1 < 1e-2 and rel1 > 20 * rel3         # really a lower-precision pass, not the same kernel path
+
+
+def test_layernorm_and_attention_vs_torch():
+    g = torch.Generator(device=DEV).manual_seed(1)
+    for m, d in ((101 * 3, 576), (50, 144), (257, 768), (16, 512)):
+        x = torch.randn((m, d), generator=g, device=DEV) * 2 + 0.3
+        gam = torch.randn(d, generator=g, device=DEV)
+        bet = torch.randn(d, generator=g, device=DEV)
+        want = torch.nn.functional.layer_norm(x.double(), (d,), gam.double(), bet.double(), 1e-6)
+        got = _unsplit(ops.layernorm_split(x, gam, bet, 1e-6))
+        assert (got - want).abs().max().item() < 3e-5 * max(1.0, want.abs().max().item())
+    for cells, tokens, heads, hd in ((3, 101, 12, 48), (2, 101, 12, 12), (4, 101, 12, 24), (2, 101, 12, 32), (5, 7, 12, 64), (3, 16, 8, 64)):
+        d = heads * hd
+        qkv = torch.randn((cells * tokens, 3 * d), generator=g, device=DEV)
+        q, k, v = qkv.view(cells, tokens, 3, heads, hd).permute(2, 0, 3, 1, 4).double().unbind(0)
+        want = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(cells * tokens, d)
+        got = _unsplit(ops.attention(qkv, cells, tokens, heads))
+        err = (got - want).abs().max().item()
+        print(f"attention cells={cells} tokens={tokens} hd={hd}: max|err|={err:.3e}")
+        assert err < 2e-5
+
+
+def _vit_pair(panel, seed=1):
+    sd = weights.random_vit_state(panel, seed=seed)
+    ref = orc.make_vit(panel)
+    ref.load_state_dict(sd)
+    return sd, ref
+
+
+@pytest.mark.parametrize("panel", ["immune_base", "nerve_cell"])
+def test_vit_reference_golden(golden_dir, panel):
+    g = np.load(os.path.join(golden_dir, "vit.npz"))
+    sd, _ = _vit_pair(panel)
+    eng = engine.VitEngine(panel, sd, DEV)
+    x = torch.from_numpy(g[panel + "_x"]).to(DEV)
+    for prec, tol_logit, tol_prob in (("bf16x3", 2e-4, 1e-4), ("simt", 5e-5, 2e-5)):
+        probs, logits = eng.forward(x, return_logits=True, precision=prec)
+        dl = np.abs(logits.cpu().numpy() - g[panel + "_logits"]).max()
+        dp = np.abs(probs.cpu().numpy() - g[panel + "_probs"]).max()
+        print(f"{panel} {prec}: max|dlogit|={dl:.3e} max|dprob|={dp:.3e}")
+        assert dl < tol_logit and dp < tol_prob
+
+
+@pytest.mark.parametrize("panel", ["immune_base", "immune_extended", "immune_full", "structure", "nerve_cell"])
+def test_vit_vs_oracle_on_real_patches(panel):
+    spec = weights.VIT_SPECS[panel]
+    mask = synth.synth_mask(160, 160, seed=6)
+    img = orc.normalize(synth.to_uint16(synth.synth_image(mask, spec.in_chans, seed=6)), 0.3, 99.8)
+    patches, _, _ = orc.build_patches(img, mask.numpy(), list(range(spec.in_chans)))
+    sd, ref = _vit_pair(panel, seed=3)
+    with torch.no_grad():
+        mean_logits = ref(torch.from_numpy(patches[:32])).mean(0).numpy()
+    sd = weights.calibrate_head(sd, mean_logits, 20.0)
+    ref.load_state_dict(sd)
+    want = orc.vit_probs(ref, patches)
+    eng = engine.VitEngine(panel, sd, DEV, max_cells_per_call=50)      # exercises chunking
+    got = eng.forward(torch.from_numpy(patches).to(DEV)).cpu().numpy()
+    dp = np.abs(got - want).max()
+    flips = int((got.argmax(1) != want.argmax(1)).sum())
+    gap = np.sort(want, 1)
+    gap = gap[:, -1] - gap[:, -2]
+    print(f"{panel}: cells={len(want)} max|dprob|={dp:.3e} argmax flips={flips} min top-2 gap={gap.min():.3e} "
+          f"label histogram={np.bincount(want.argmax(1), minlength=want.shape[1]).tolist()}")
+    assert dp < 1e-3
+    assert flips <= int((gap < 2 * dp).sum())          # a flip is only possible inside the error band
+
+
+@pytest.mark.parametrize("panel,present", [("immune_base", [0, 1, 2, 3, 4, 6]), ("immune_extended", [0, 1, 2, 4, 5, 6, 7, 9]),
+                                           ("immune_full", [0, 1, 2, 3, 4, 6, 7, 8, 9, 11, 13, 14])])
+def test_mae_vs_oracle_and_golden(golden_dir, panel, present):
+    sd = weights.random_mae_state(panel, seed=1)
+    eng = engine.MaeEngine(panel, sd, DEV)
+    g = np.load(os.path.join(golden_dir, "mae.npz"))
+    if panel + "_x" in g:
+        x, want = g[panel + "_x"], g[panel + "_out"]
+    else:
+        spec = weights.MAE_SPECS[panel]
+        gen = torch.Generator().manual_seed(8)
+        x = (torch.rand((4, spec.channels, 40, 40), generator=gen) * 2 - 1).numpy()
+        x[:, [c for c in range(spec.channels) if c not in present]] = -1
+        ref = orc.make_mae(panel)
+        ref.load_state_dict(sd)
+        want = orc.impute(ref, x, present)
+    got = eng.impute(torch.from_numpy(x.copy()).to(DEV), present).cpu().numpy()
+    for c in present:
+        assert np.array_equal(got[:, c], x[:, c])
+    d = np.abs(got - want).max()
+    print(f"mae {panel}: max|d|={d:.3e} range of imputed values [{want.min():.3f}, {want.max():.3f}]")
+    assert d < 1e-3
+
+
+@pytest.mark.parametrize("tag,strict", [("full", True), ("impute", False), ("struct_nerve", True)])
+def test_annotator_end_to_end_golden(golden_dir, tag, strict, tmp_path, monkeypatch):
+    """Annotator.preprocess() + predict() + export_annotations() against the reference's own run."""
+    g = np.load(os.path.join(golden_dir, "e2e.npz"))
+    monkeypatch.chdir(tmp_path)
+    np.save("img.npy", g[tag + "_img"])
+    np.save("mask.npy", g[tag + "_mask"])
+    markers = [str(m) for m in g[tag + "_markers"]]
+    synth.write_marker_file("markers.txt", markers)
+    with open("images.csv", "w") as f:
+        f.write("image_path,mask_path\nimg.npy,mask.npy\n")
+    for panel in weights.VIT_SPECS:
+        key = f"{tag}_meanlogits_{panel}"
+        sd = weights.random_vit_state(panel, seed=2)
+        if key in g:
+            sd = weights.calibrate_head(sd, g[key], 20.0)
+        bmodel.register_state(panel, sd)
+    bimputer.register_state("immune_base", weights.random_mae_state("immune_base", seed=2))
+    ann = bmodel.Annotator("markers.txt", "images.csv", "cuda", "./", "g", strict, True, -1, True, 0.3, 99.8, 0.3, 30, None, n_jobs=0)
+    ann.preprocess()
+    ann.predict(32)
+    ann.export_annotations()
+    # stages 1-3: bit-exact patches (the imputed channels within the network tolerance)
+    for panel, pt in ann.preprocessor.patches[0].items():
+        want = g[f"{tag}_patches_{panel}"]
+        got = pt.cpu().numpy()
+        if tag == "impute":
+            assert np.array_equal(got[:, [0, 1, 2, 3, 4, 6]], want[:, [0, 1, 2, 3, 4, 6]])
+            assert np.abs(got - want).max() < 1e-3
+        else:
+            assert np.array_equal(got, want)
+    np.testing.assert_allclose(ann.preprocessor.intensity_full[0], g[tag + "_intensity"], rtol=1e-12, atol=1e-14)
+    # stage 4: probabilities within 1e-3 of the reference
+    worst = 0.0
+    for panel, p in ann.probs[0].items():
+        worst = max(worst, float(np.abs(p - g[f"{tag}_probs_{panel}"]).max()))
+    print(f"e2e {tag}: max|dprob|={worst:.3e}")
+    assert worst < 1e-3
+    # stage 5 + result assembly: labels exact, confidences within the probability tolerance, CSV identical
+    # wherever the printed 3-decimal confidence is not on a rounding boundary
+    assert ann.annotations[0] == g[tag + "_labels"].tolist()
+    conf = np.array([float(c) for c in ann.confidence[0]])
+    assert np.abs(conf - g[tag + "_conf"]).max() < 1e-3
+    assert [str(c) for c in ann.cell_types] == g[tag + "_cell_types"].tolist()
+    got_rows = open("results/g_annotation_0.csv").read().strip().split("\n")
+    want_rows = str(g[tag + "_csv"]).strip().split("\n")
+    assert got_rows[0] == want_rows[0] and len(got_rows) == len(want_rows)
+    for a, b in zip(got_rows[1:], want_rows[1:]):
+        fa, fb = a.split(","), b.split(",")
+        assert fa[:2] == fb[:2] and fa[3:] == fb[3:], (a, b)            # id, type, centroid, region identical
+        assert abs(float(fa[2]) - float(fb[2])) <= 1.001e-3
+    comp = ann.cell_type_composition(reduction=False)[0]
+    assert sum(comp.values()) == len(ann.annotations[0])
+    ann.clear_tmp()
+    assert not os.path.exists("tmp")

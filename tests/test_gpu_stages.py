@@ -1,0 +1,196 @@
+"""GPU parity tests for stages 1-3 and 5: the CUDA path (through the C ABI) against the golden
+fixtures produced by the reference and against the CPU oracle on seeded inputs.
+Bit-exact for integer work AND for the float32 stage outputs (the kernels follow scipy's / numpy's
+operation order); 1e-12 relative for the float64 per-cell mean intensities (different summation tree)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ribca_oracle as orc                                  # checker only
+from multiplexed_image_annotator_b200 import ops, synth                  # noqa: E402
+
+DEV = "cuda"
+
+
+def _npz(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _report_mismatch(name, got, want):
+    bad = np.argwhere(got != want)
+    msg = f"{name}: {len(bad)} / {got.size} elements differ"
+    if len(bad):
+        i = tuple(bad[0])
+        msg += f"; first at {i}: got {got[i]!r} want {want[i]!r}; max|d| {np.abs(got.astype(np.float64) - want).max():.3e}"
+    return msg
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 2
+# ------------------------------------------------------------------------------------------------
+def _check_stats(mask_np):
+    want = orc.cell_stats(mask_np)
+    tab = ops.cell_stats(torch.from_numpy(mask_np.astype(np.int32)).to(DEV))
+    assert tab.n == len(want["ids"])
+    assert np.array_equal(tab.ids.cpu().numpy(), want["ids"])
+    assert np.array_equal(tab.bbox.cpu().numpy(), want["bbox"]), _report_mismatch("bbox", tab.bbox.cpu().numpy(), want["bbox"])
+    assert np.array_equal(tab.sums.cpu().numpy(), np.stack([want["sum_r"], want["sum_c"]], 1))
+    assert np.array_equal(tab.count.cpu().numpy(), want["count"])
+    assert np.array_equal(tab.centroids().cpu().numpy(), orc.centroids(want))       # float64, bit-exact
+    idx = tab.id_to_index.cpu().numpy()
+    assert np.array_equal(np.nonzero(idx >= 0)[0], want["ids"])
+    return tab
+
+
+@pytest.mark.parametrize("fixture", ["cells_example2.npz", "cells_example1_crop.npz"])
+def test_cell_stats_reference_golden(golden_dir, fixture):
+    g = _npz(golden_dir, fixture)
+    tab = _check_stats(g["mask"].astype(np.int32))
+    t = g["table"]
+    assert np.array_equal(tab.ids.cpu().numpy(), t[:, 0])
+    assert np.array_equal(tab.bbox.cpu().numpy(), t[:, 1:5])
+    assert np.array_equal(tab.sums.cpu().numpy(), t[:, 5:7])
+    assert np.array_equal(tab.count.cpu().numpy(), t[:, 7])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 13), (64, 64), (257, 1031), (1000, 1200)])
+def test_cell_stats_ragged_masks(shape):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    h, w = shape
+    mask = np.zeros(shape, np.int32)
+    # sparse non-contiguous labels, 1-pixel cells, cells touching every border
+    labels = rng.choice(np.arange(1, 50000), size=max(1, h * w // 40), replace=False)
+    for lab in labels:
+        r, c = rng.integers(0, h), rng.integers(0, w)
+        rh, cw = rng.integers(1, 9), rng.integers(1, 9)
+        mask[r:r + rh, c:c + cw] = lab
+    mask[0, 0] = 49999 + 1
+    mask[h - 1, w - 1] = 7
+    _check_stats(mask)
+
+
+def test_cell_stats_large_synthetic():
+    mask = synth.synth_mask(2048, 2048, seed=5).numpy()
+    tab = _check_stats(mask)
+    assert tab.n > 12000
+
+
+def test_cell_stats_empty_mask():
+    tab = ops.cell_stats(torch.zeros((33, 47), dtype=torch.int32, device=DEV))
+    assert tab.n == 0 and tab.ids.numel() == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 1
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,blur,amax", [("b03_a998", 0.3, 99.8), ("b0_a100", 0, 100), ("b1_a100", 1, 100),
+                                           ("b04_a95", 0.4, 95.0)])
+def test_normalize_reference_golden(golden_dir, tag, blur, amax):
+    g = _npz(golden_dir, "normalize.npz")
+    got = ops.normalize(torch.from_numpy(g["img"]).to(DEV), blur, amax).cpu().numpy()
+    assert np.array_equal(got, g[tag]), _report_mismatch(tag, got, g[tag])
+    got = ops.normalize(torch.from_numpy(g["img_f32"]).to(DEV), blur, amax).cpu().numpy()
+    assert np.array_equal(got, g["f32_" + tag]), _report_mismatch("f32_" + tag, got, g["f32_" + tag])
+
+
+@pytest.mark.parametrize("shape,dtype", [((3, 300, 517), np.uint16), ((2, 64, 64), np.uint8), ((1, 700, 90), np.float32)])
+def test_normalize_vs_oracle(shape, dtype):
+    rng = np.random.default_rng(11)
+    c, h, w = shape
+    mask = synth.synth_mask(h, w, seed=3)
+    img = synth.synth_image(mask, c, seed=3).numpy()
+    if dtype == np.uint8:
+        img = (img // 16).clip(0, 255)
+    img = img.astype(dtype)
+    want = orc.normalize(img, 0.3, 99.8)
+    got, stats = ops.normalize(torch.from_numpy(img).to(DEV), 0.3, 99.8, return_stats=True)
+    got = got.cpu().numpy()
+    assert np.array_equal(got, want), _report_mismatch("normalize", got, want)
+    mn = ops.channel_min(torch.from_numpy(want).to(DEV)).cpu().numpy()
+    assert np.array_equal(mn, want.min(axis=(1, 2)))
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 3
+# ------------------------------------------------------------------------------------------------
+def _gpu_patches(image, mask, index, n=None):
+    img = torch.from_numpy(np.ascontiguousarray(image)).to(DEV)
+    m = torch.from_numpy(np.ascontiguousarray(mask.astype(np.int32))).to(DEV)
+    tab = ops.cell_stats(m)
+    mn = ops.channel_min(img)
+    outs, avg, wins = ops.build_patches(img, m, mn, tab, [index], 0, n, want_intensity=True, want_windows=True)
+    return outs[0].cpu().numpy(), (avg.cpu().numpy() + 1) / 2, wins.cpu().numpy(), tab
+
+
+@pytest.mark.parametrize("tag,maskkey", [("synth", "mask"), ("synth_q3", "mask"), ("real", "mask_real")])
+def test_patches_reference_golden(golden_dir, tag, maskkey):
+    g = _npz(golden_dir, "patches.npz")
+    mask = g[maskkey]
+    image = g["img_norm"][:, : mask.shape[0], : mask.shape[1]]
+    pt, inten, wins, tab = _gpu_patches(image, mask, g[tag + "_index"].tolist())
+    assert np.array_equal(tab.ids.cpu().numpy(), g[tag + "_ids"])
+    assert np.array_equal(wins, g[tag + "_windows"]), _report_mismatch("windows", wins, g[tag + "_windows"])
+    n = len(g[tag + "_patches"])
+    assert np.array_equal(pt[:n], g[tag + "_patches"]), _report_mismatch("patches", pt[:n], g[tag + "_patches"])
+    np.testing.assert_allclose(inten, g[tag + "_intensity"], rtol=1e-12, atol=1e-14)
+
+
+def test_patches_vs_oracle_border_cells():
+    h, w = 97, 131                                    # windows truncated at every border
+    mask = synth.synth_mask(h, w, grid=14, seed=9, r_lo=3, r_hi=7).numpy()
+    mask[0:3, 0:4] = 9001                             # corner cells
+    mask[h - 2:, w - 3:] = 9002
+    mask[50, 60] = 9003                               # 1-pixel cell
+    img = synth.to_uint16(synth.synth_image(torch.from_numpy(mask), 6, seed=9))
+    norm = orc.normalize(img, 0.3, 99.8)
+    index = [5, 0, -1, 3, 1]
+    want, w_int, w_win = orc.build_patches(norm, mask, index)
+    pt, inten, wins, _ = _gpu_patches(norm, mask, index)
+    assert np.array_equal(wins, w_win)
+    assert np.array_equal(pt, want), _report_mismatch("patches", pt, want)
+    np.testing.assert_allclose(inten, w_int, rtol=1e-12, atol=1e-14)
+
+
+def test_patches_multi_panel_and_chunks():
+    mask = synth.synth_mask(200, 200, seed=4).numpy()
+    img = orc.normalize(synth.to_uint16(synth.synth_image(torch.from_numpy(mask), 8, seed=4)), 0.3, 99.8)
+    it = torch.from_numpy(img).to(DEV)
+    mt = torch.from_numpy(mask).to(DEV)
+    tab = ops.cell_stats(mt)
+    mn = ops.channel_min(it)
+    panels = [[0, 1, 2], [7, -1, 5, 4, -1, 3, 2], [6]]
+    full, _, _ = ops.build_patches(it, mt, mn, tab, panels)
+    for p, chans in enumerate(panels):
+        want, _, _ = orc.build_patches(img, mask, chans, cells=range(0, 30))
+        assert np.array_equal(full[p][:30].cpu().numpy(), want)
+    part, _, _ = ops.build_patches(it, mt, mn, tab, panels, cell_begin=17, n_cells=40)
+    for p in range(3):
+        assert torch.equal(part[p], full[p][17:57])
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 5
+# ------------------------------------------------------------------------------------------------
+def test_merge_reference_golden(golden_dir):
+    from multiplexed_image_annotator_b200.cell_type_annotation.model import merge_on_device, ALL_TYPES
+    cases = json.load(open(os.path.join(golden_dir, "merge.json")))
+    checked = 0
+    for case in cases:
+        probs = {k: torch.tensor(v, dtype=torch.float32, device=DEV) for k, v in case["probs"].items()}
+        if "raises" in case:
+            with pytest.raises(KeyError):
+                merge_on_device(probs, case["confidence"], case["ctc"])
+            continue
+        label, conf, counts = merge_on_device(probs, case["confidence"], case["ctc"])
+        names = [ALL_TYPES[i] for i in label.cpu().tolist()]
+        assert names == case["labels"], (case["panels"], case["confidence"])
+        assert np.array_equal(conf.cpu().numpy().astype(np.float64), np.array(case["conf"]))
+        want_counts = np.bincount([ALL_TYPES.index(n) for n in case["labels"]], minlength=18)
+        assert np.array_equal(counts.cpu().numpy(), want_counts)
+        checked += 1
+    assert checked >= 30

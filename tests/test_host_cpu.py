@@ -1,0 +1,171 @@
+"""CPU-only tests: the C-ABI library builds, loads and exports every declared symbol; host-side plans
+match numpy / scipy; the reference-facing host classes behave like the reference (golden fixtures);
+the multi-rank partition + gather logic works over gloo with world_size 2."""
+import contextlib
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from multiplexed_image_annotator_b200 import _lib, ops, parallel, synth, weights
+from multiplexed_image_annotator_b200.cell_type_annotation.markerParse import MarkerParser
+from multiplexed_image_annotator_b200.cell_type_annotation import model as bmodel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    _lib.build()
+    header = open(os.path.join(ROOT, "include", "ribca_b200.h")).read()
+    declared = set(re.findall(r"\b(ribca_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ribca_stream_t"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()                         # raises AttributeError if a symbol is missing
+    assert lib.ribca_version() >= 100
+    nm = subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ribca_[a-z0-9_]+)", nm))
+    assert declared <= exported
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    _lib.build()
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "gemm_tcgen05_kernel", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if "UTCHMMA" not in sass:               # -fun needs the mangled name on some toolkits: fall back to everything
+        sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+
+
+def test_ops_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.normalize(torch.zeros((1, 8, 8), dtype=torch.uint16))
+    with pytest.raises(RuntimeError):
+        ops.cell_stats(torch.zeros((8, 8), dtype=torch.int32))
+
+
+def test_percentile_plan_matches_numpy():
+    rng = np.random.default_rng(0)
+
+    def lerp32(a, b, g):
+        a, b, g = np.float32(a), np.float32(b), np.float32(g)
+        d = np.float32(b - a)
+        r = np.float32(a + np.float32(d * g))
+        if g >= 0.5:
+            r = np.float32(b - np.float32(d * np.float32(np.float32(1) - g)))
+        return r
+
+    for n in (1, 2, 3, 10, 1000, 19650, 123457, 17_000_001):
+        x = np.maximum(rng.normal(size=n).astype(np.float32) * 50, 0)
+        xs = np.sort(x)
+        for amax in (99.8, 100, 95.0, 50, 0, 99.99):
+            k_lo, k_hi, g = ops.percentile_plan(n, amax)
+            assert np.percentile(x, amax) == lerp32(xs[k_lo], xs[k_hi], g), (n, amax)
+
+
+def test_gaussian_taps_match_scipy():
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    for s in (20, 0.3, 0.4, 1, 2, 3):
+        w, r = ops.gaussian_half_kernel(s)
+        full = _gaussian_kernel1d(s, 0, r)[::-1]
+        assert r == int(4.0 * float(s) + 0.5) and np.array_equal(full[r:], w)
+
+
+def test_marker_parser_matches_reference(golden_dir, tmp_path):
+    cases = json.load(open(os.path.join(golden_dir, "markers.json")))
+    for name, case in cases.items():
+        f = tmp_path / f"{name}.txt"
+        f.write_text("\n".join(case["markers"]) + "\n")
+        p = MarkerParser(strict=case["strict"], logger=None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            if "raises" in case:
+                with pytest.raises(TypeError):
+                    p.parse(str(f))
+                continue
+            p.parse(str(f))
+        assert p.indices == case["indices"], name
+        assert [p.immune_base, p.immune_extended, p.immune_full, p.struct, p.nerve] == case["flags"]
+        assert [str(m) for m in p.markers] == case["parsed_markers"] and p.n_markers == case["n_markers"]
+
+
+def test_merge_branch_matches_reference_elif_chain(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "merge.json")))
+    for case in cases:
+        if "raises" in case:
+            with pytest.raises(KeyError):
+                bmodel.merge_branch(case["panels"])
+        else:
+            used = bmodel.merge_branch(case["panels"])
+            assert 1 <= len(used) <= 2 and set(used) <= set(case["panels"])
+    with pytest.raises(ValueError):
+        bmodel.merge_branch([])
+
+
+def test_random_weights_fit_the_reference_architectures():
+    from oracle import ribca_oracle as orc
+    for panel in weights.VIT_SPECS:
+        orc.make_vit(panel).load_state_dict(weights.random_vit_state(panel, seed=0), strict=True)
+    orc.make_mae("immune_base").load_state_dict(weights.random_mae_state("immune_base", seed=0), strict=True)
+    tab = weights.sincos_table(512, (2, 5))
+    np.testing.assert_allclose(tab[0].numpy(), orc.sincos_2d(512, (2, 5)), atol=1e-6)
+
+
+def test_synthetic_scene_generator():
+    mask = synth.synth_mask(180, 200, seed=2)
+    assert mask.dtype == torch.int32 and mask.shape == (180, 200)
+    ids = torch.unique(mask)
+    assert ids[0] == 0 and len(ids) > 80
+    img = synth.to_uint16(synth.synth_image(mask, 4, seed=2))
+    assert img.shape == (4, 180, 200) and img.dtype == np.uint16 and img.max() > 500
+    assert torch.equal(mask, synth.synth_mask(180, 200, seed=2))
+
+
+def test_shard_range_is_a_balanced_partition():
+    for n in (0, 1, 7, 100, 51843):
+        for w in (1, 2, 3, 8):
+            parts = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from multiplexed_image_annotator_b200 import parallel
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = parallel.world()
+n = 11
+lo, hi = parallel.shard_range(n, rank, world)
+label = torch.arange(lo, hi, dtype=torch.uint8)
+conf = torch.arange(lo, hi, dtype=torch.float32) * 0.5
+full_l = parallel.all_gather_rows(label, n, lo, hi)
+full_c = parallel.all_gather_rows(conf, n, lo, hi)
+counts = parallel.all_reduce_sum(torch.tensor([hi - lo, 1], dtype=torch.int64))
+assert full_l.tolist() == list(range(n)), full_l
+assert full_c.tolist() == [0.5 * i for i in range(n)]
+assert counts.tolist() == [n, 2]
+mat = parallel.all_gather_rows(torch.full((hi - lo, 3), float(rank)), n, lo, hi)
+assert mat.shape == (n, 3) and mat[:6].eq(0).all() and mat[6:].eq(1).all()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gather_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in out, out
