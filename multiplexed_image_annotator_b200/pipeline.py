@@ -1,0 +1,89 @@
+"""In-memory entry point of the hot path: decoded image + label mask in, labels / confidences /
+per-type counts out.  This is the call `bench.py` times end to end (host buffers in, host results
+out) and the sequence `Annotator.preprocess()` + `Annotator.predict()` runs per image
+(reference cta/preprocess.py:241-290, cta/model.py:431-453), without the file and plotting layers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ops
+from .cell_type_annotation.model import ALL_TYPES, merge_on_device
+from .engine import MaeEngine, VitEngine
+from .parallel import all_gather_rows, all_reduce_sum, shard_range, world
+
+
+@dataclass
+class HotPathResult:
+    n_cells: int
+    label: torch.Tensor            # uint8 (n,) index into ALL_TYPES
+    confidence: torch.Tensor       # float32 (n,), -1 where re-labelled "Others"
+    counts: torch.Tensor           # int64 (18,)
+    probs: dict = field(default_factory=dict)
+    cells: object = None
+
+    def names(self):
+        return [ALL_TYPES[k] for k in self.label.cpu().tolist()]
+
+
+class HotPath:
+    """Stages 1-5 for one image.  `panels` maps panel name -> channel index list (MarkerParser.indices
+    restricted to the panels that predict consumes); `models` maps panel -> VitEngine; `imputers`
+    maps panel -> (MaeEngine, present positions) for panels with a missing marker."""
+
+    def __init__(self, panels: dict, models: dict, imputers: dict | None = None, *, normalization=True, blur=0.3,
+                 amax=99.8, confidence=0.3, cell_type_confidence=None, chunk_cells=4096, device="cuda",
+                 shard_cells=True):
+        self.panels, self.models, self.imputers = dict(panels), models, imputers or {}
+        self.normalization, self.blur, self.amax = normalization, blur, amax
+        self.confidence, self.ctc = confidence, cell_type_confidence
+        self.chunk = chunk_cells
+        self.device = torch.device(device)
+        self.shard_cells = shard_cells
+        for p in self.panels:
+            if not isinstance(models.get(p), VitEngine):
+                raise ValueError(f"no classifier engine for panel {p}")
+
+    def _to_device(self, a):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(a)
+        return a if a.is_cuda else a.to(self.device, non_blocking=True)
+
+    @torch.no_grad()
+    def run(self, image, mask, to_host: bool = True, keep_probs: bool = False) -> HotPathResult:
+        img = self._to_device(image)
+        msk = self._to_device(mask)
+        if msk.dtype != torch.int32:
+            msk = msk.to(torch.int32)
+        if self.normalization:
+            img = ops.normalize(img, self.blur, self.amax)
+        elif img.dtype != torch.float32:
+            img = img.to(torch.float32)
+        cells = ops.cell_stats(msk)
+        mn = ops.channel_min(img)
+        rank, nranks = world() if self.shard_cells else (0, 1)
+        lo, hi = shard_range(cells.n, rank, nranks)
+        names = list(self.panels)
+        idx = [self.panels[p] for p in names]
+        parts = {p: [] for p in names}
+        for a in range(lo, hi, self.chunk):
+            b = min(a + self.chunk, hi)
+            outs, _, _ = ops.build_patches(img, msk, mn, cells, idx, a, b - a)
+            for p, t in zip(names, outs):
+                if p in self.imputers:
+                    eng, present = self.imputers[p]
+                    eng.impute(t, present)
+                parts[p].append(self.models[p].forward(t))
+        probs = {p: (torch.cat(v) if v else torch.empty((0, len(self.models[p].spec.classes)), device=self.device))
+                 for p, v in parts.items()}
+        label, conf, counts = merge_on_device(probs, self.confidence, self.ctc)
+        if nranks > 1:
+            label = all_gather_rows(label, cells.n, lo, hi)
+            conf = all_gather_rows(conf, cells.n, lo, hi)
+            counts = all_reduce_sum(counts)
+        if to_host:
+            label, conf, counts = label.cpu(), conf.cpu(), counts.cpu()     # D2H ends the step (synchronises)
+        return HotPathResult(cells.n, label, conf, counts, probs if keep_probs else {}, cells)
