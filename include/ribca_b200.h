@@ -149,9 +149,10 @@ int ribca_build_patches(const float* img, const int32_t* mask, int C_img, int H,
  *   epilogue: v = acc + (bias ? bias[col] : 0) + (row_table ? row_table[(row % table_period)*N + col] : 0)
  *     RIBCA_EPI_STORE    out_f32[row*N+col]  = v
  *     RIBCA_EPI_RESIDUAL out_f32[row*N+col] += v
- *     RIBCA_EPI_GELU     out split-bf16 {hi, lo}[row*N+col] = gelu_erf(v), plane stride out_plane
+ *     RIBCA_EPI_GELU        out split-bf16 {hi, lo}[row*N+col] = gelu_erf(v), plane stride out_plane
+ *     RIBCA_EPI_STORE_SPLIT out split-bf16 {hi, lo}[row*N+col] = v
  */
-enum ribca_epilogue { RIBCA_EPI_STORE = 0, RIBCA_EPI_RESIDUAL = 1, RIBCA_EPI_GELU = 2 };
+enum ribca_epilogue { RIBCA_EPI_STORE = 0, RIBCA_EPI_RESIDUAL = 1, RIBCA_EPI_GELU = 2, RIBCA_EPI_STORE_SPLIT = 3 };
 int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long long w_plane,
                          int M, int N, int K, const float* bias, const float* row_table,
                          int table_period, int epilogue, float* out_f32, void* out_split,
@@ -162,9 +163,14 @@ int ribca_split_bf16(const float* x, long long n, void* hi, void* lo, ribca_stre
 /* row LayerNorm(eps) of x[M][D] -> split-bf16 planes (plane stride out_plane elements) */
 int ribca_layernorm_split(const float* x, int M, int D, const float* gamma, const float* beta,
                           float eps, void* out_split, long long out_plane, ribca_stream_t stream);
-/* multi-head self-attention over qkv[cells][tokens][3][heads][hd] (fp32) -> split-bf16 [M][D] */
+/* multi-head self-attention over qkv[cells][tokens][3][heads][hd] (fp32) -> split-bf16 [M][D];
+ * FP32-pipe kernel, used for the short sequences of the imputer (tokens <= 32) */
 int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head_dim,
                     void* out_split, long long out_plane, ribca_stream_t stream);
+/* the same on the tensor cores (tcgen05, split-bf16 passes) for tokens <= 128: qkv_split is
+ * [2][M][3][heads][hdp] bf16 with hdp = head_dim rounded up to 16 and exact zeros in the padding */
+int ribca_attention_tc(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads,
+                       int head_dim, void* out_split, long long out_plane, ribca_stream_t stream);
 
 /* Classifier: device-resident weights in the layout produced by the host packer
  * (multiplexed_image_annotator_b200/engine.py: pack_vit); all offsets in `desc` are element
@@ -174,6 +180,8 @@ typedef struct ribca_block_desc {
   long long qkv_b, proj_b, fc1_b, fc2_b;           /* wf32 */
   long long qkv_w, proj_w, fc1_w, fc2_w;           /* wsplit */
 } ribca_block_desc;
+/* qkv_w / qkv_b are stored head-padded: [3][heads][hdp][D] and [3][heads][hdp] with hdp = head_dim
+ * rounded up to a multiple of 16 and zero rows in the padding (hdp == head_dim for 32 / 48 / 64). */
 
 typedef struct ribca_vit_desc {
   int dim, heads, depth, in_chans, classes, tokens;  /* tokens = 101 */

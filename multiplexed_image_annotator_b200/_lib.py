@@ -119,6 +119,7 @@ SIGNATURES = {
     "ribca_split_bf16": (_I, [_P, _LL, _P, _P, _P]),
     "ribca_layernorm_split": (_I, [_P, _I, _I, _P, _P, _F, _P, _LL, _P]),
     "ribca_attention": (_I, [_P, _I, _I, _I, _I, _P, _LL, _P]),
+    "ribca_attention_tc": (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _P]),
     "ribca_vit_workspace_bytes": (_SZ, [C.POINTER(VitDesc), _I]),
     "ribca_vit_forward": (_I, [C.POINTER(VitDesc), _P, _P, _P, _I, _P, _P, _P, _SZ, _I, _P]),
     "ribca_mae_workspace_bytes": (_SZ, [C.POINTER(MaeDesc), _I]),

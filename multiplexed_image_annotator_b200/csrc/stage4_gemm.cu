@@ -20,9 +20,7 @@
 //                overlaps the main loop of tile t+1
 //   tiles are ordered m-major so the CTAs of one wave share A rows through L2 and W stays L2-resident.
 #include "common.cuh"
-
-#include <cuda.h>
-#include <cudaTypedefs.h>
+#include "sm100_ptx.cuh"
 
 namespace ribca {
 
@@ -55,96 +53,6 @@ struct GemmShape {
   int a_plane[3];           // plane index of A per pass
   int w_plane[3];
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (bf16 in, fp32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) ;
-//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups ; [46,48) version = 1 ;
-//   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
-// K-major A and B (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
-__device__ __forceinline__ uint32_t make_instr_desc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -205,7 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(BN);
+      const uint32_t idesc = make_instr_desc(BM, BN);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
@@ -265,10 +173,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           const long long o = (long long)row * shp.N + col;
-          if (epi.mode == RIBCA_EPI_GELU) {
+          if (epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT) {
             __align__(16) __nv_bfloat16 hi[16], lo[16];
+            if (epi.mode == RIBCA_EPI_GELU) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split_bf16(gelu_erf(v[i]), hi[i], lo[i]);
+              for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_bf16(v[i], hi[i], lo[i]);
             uint4* ph = reinterpret_cast<uint4*>(epi.out_hi + o);
             uint4* pl = reinterpret_cast<uint4*>(epi.out_lo + o);
             ph[0] = reinterpret_cast<const uint4*>(hi)[0]; ph[1] = reinterpret_cast<const uint4*>(hi)[1];
@@ -355,6 +267,8 @@ gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, long long a_plane, const _
       const long long o = (long long)row * shp.N + col;
       if (epi.mode == RIBCA_EPI_GELU) {
         split_bf16(gelu_erf(v), epi.out_hi[o], epi.out_lo[o]);
+      } else if (epi.mode == RIBCA_EPI_STORE_SPLIT) {
+        split_bf16(v, epi.out_hi[o], epi.out_lo[o]);
       } else if (epi.mode == RIBCA_EPI_RESIDUAL) {
         epi.out_f32[o] += v;
       } else {
@@ -372,21 +286,9 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n, __nv
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
-}
-
 // 3-D map over a split operand: dims (K, rows, 2 planes), box (64, box_rows, 1), 128B swizzle
 static int make_operand_map(CUtensorMap* map, const void* base, long long plane_elems, int rows, int K, int box_rows) {
-  auto encode = get_encode_fn();
+  auto encode = tensor_map_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return RIBCA_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_elems * 2};
@@ -414,7 +316,8 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   RIBCA_REQUIRE(A && W, "gemm: null operand");
   RIBCA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RIBCA_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm: N=%d must be a multiple of 16 and K=%d of 8", N, K);
-  RIBCA_REQUIRE(epilogue == RIBCA_EPI_GELU ? (out_split != nullptr) : (out_f32 != nullptr), "gemm: output is null");
+  const bool split_out = epilogue == RIBCA_EPI_GELU || epilogue == RIBCA_EPI_STORE_SPLIT;
+  RIBCA_REQUIRE(split_out ? (out_split != nullptr) : (out_f32 != nullptr), "gemm: output is null");
   RIBCA_REQUIRE(!row_table || table_period > 0, "gemm: row table needs a period");
   RIBCA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                     (a_plane * 2) % 16 == 0 && (w_plane * 2) % 16 == 0,

@@ -14,6 +14,9 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
                 const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
                 void* out_split, long long out_plane, int precision, cudaStream_t stream);
 
+int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads, int hd,
+                        void* out_split, long long out_plane, cudaStream_t st);
+
 typedef __nv_bfloat16 bf16;
 
 // ---- patches -> patch-embed A operand ---------------------------------------------------------
@@ -350,12 +353,24 @@ static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int head
                       int precision, cudaStream_t st) {
   const int M = cells * tokens;
   const long long pa = (long long)M * D, ph = (long long)M * 4 * D;
+  const int hd = D / heads, hdp = (hd + 15) / 16 * 16;
+  const int Wq = 3 * heads * hdp;                       // head-padded qkv width
+  const bool tensor_attention = tokens > 32;            // tcgen05 for the classifiers, FP32 pipe for the imputer
+  RIBCA_REQUIRE(tensor_attention || hdp == hd, "short-sequence attention needs head_dim %% 16 == 0");
   for (int l = 0; l < depth; ++l) {
     const ribca_block_desc& w = blocks[l];
     RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln1_g, wf32 + w.ln1_b, 1e-6f, b.a, pa, st));
-    RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, 3 * D, D, wf32 + w.qkv_b, nullptr, 0,
-                          RIBCA_EPI_STORE, b.qkv, nullptr, 0, precision, st));
-    RIBCA_TRY(attention_launch(b.qkv, cells, tokens, heads, D / heads, b.a, pa, st));
+    if (tensor_attention) {
+      bf16* qs = reinterpret_cast<bf16*>(b.qkv);
+      const long long pq = (long long)M * Wq;
+      RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
+                            RIBCA_EPI_STORE_SPLIT, nullptr, qs, pq, precision, st));
+      RIBCA_TRY(attention_tc_launch(qs, pq, cells, tokens, heads, hd, b.a, pa, st));
+    } else {
+      RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
+                            RIBCA_EPI_STORE, b.qkv, nullptr, 0, precision, st));
+      RIBCA_TRY(attention_launch(b.qkv, cells, tokens, heads, hd, b.a, pa, st));
+    }
     RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
                           RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, st));
     RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, b.a, pa, st));
@@ -377,10 +392,11 @@ struct Carver {
   }
 };
 
-static size_t block_buffers(Carver& cv, BlockBuffers& b, long long M, int D) {
+static size_t block_buffers(Carver& cv, BlockBuffers& b, long long M, int D, int heads) {
+  const int hdp = (D / heads + 15) / 16 * 16;
   b.x = cv.take<float>(M * D);
   b.a = cv.take<bf16>(2 * M * D);
-  b.qkv = cv.take<float>(M * 3 * D);
+  b.qkv = cv.take<float>(M * 3 * heads * hdp);     // fp32 [M][3D] or split-bf16 [2][M][3*heads*hdp]: same bytes
   b.h = cv.take<bf16>(2 * M * 4 * D);
   return cv.off;
 }
@@ -407,7 +423,7 @@ size_t ribca_vit_workspace_bytes(const ribca_vit_desc* desc, int n_cells) {
   if (!desc || n_cells <= 0) return 0;
   Carver cv{nullptr, 0};
   BlockBuffers b;
-  block_buffers(cv, b, (long long)n_cells * desc->tokens, desc->dim);
+  block_buffers(cv, b, (long long)n_cells * desc->tokens, desc->dim, desc->heads);
   return align_up(cv.off, 256);
 }
 
@@ -430,7 +446,7 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
   RIBCA_REQUIRE(M < (1ll << 31) / 16, "ribca_vit_forward: %d cells per call is too many; chunk the batch", n_cells);
   Carver cv{static_cast<char*>(workspace), 0};
   BlockBuffers b;
-  block_buffers(cv, b, M, D);
+  block_buffers(cv, b, M, D, desc->heads);
   // patch embedding: im2col into the (larger) MLP buffer, GEMM with the cls/pos/bias row table
   const int Kpe = 16 * C;
   const long long pe_plane = M * Kpe;
@@ -448,8 +464,8 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
 static void mae_carve(const ribca_mae_desc* d, int n_cells, int n_present, Carver& cv, BlockBuffers& be, BlockBuffers& bd,
                       float*& emb, float*& pred, float*& table) {
   const long long Me = (long long)n_cells * (n_present + 1), Md = (long long)n_cells * (d->channels + 1);
-  block_buffers(cv, be, Me, d->enc_dim);
-  block_buffers(cv, bd, Md, d->dec_dim);
+  block_buffers(cv, be, Me, d->enc_dim, d->enc_heads);
+  block_buffers(cv, bd, Md, d->dec_dim, d->dec_heads);
   emb = cv.take<float>(Me * d->dec_dim);
   pred = cv.take<float>(Md * 1600);
   table = cv.take<float>((size_t)(n_present + 1) * d->enc_dim);

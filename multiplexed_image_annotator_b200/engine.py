@@ -47,12 +47,25 @@ class _Packer:
         return wf32, wsplit, self.mat_off
 
 
-def _pack_block(pk: _Packer, sd, prefix: str, desc: _lib.BlockDesc):
+def _pad_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
+    """qkv weight (3D, D) / bias (3D,) -> head-padded (3*heads*hdp, ...) with zero rows, hdp = ceil16(hd)."""
+    d3 = t.shape[0]
+    hd = d3 // (3 * heads)
+    hdp = (hd + 15) // 16 * 16
+    if hdp == hd:
+        return t
+    v = t.reshape(3, heads, hd, *t.shape[1:])
+    out = v.new_zeros((3, heads, hdp) + tuple(t.shape[1:]))
+    out[:, :, :hd] = v
+    return out.reshape(3 * heads * hdp, *t.shape[1:])
+
+
+def _pack_block(pk: _Packer, sd, prefix: str, desc: _lib.BlockDesc, heads: int):
     desc.ln1_g = pk.add_f32(sd[f"{prefix}.norm1.weight"]); desc.ln1_b = pk.add_f32(sd[f"{prefix}.norm1.bias"])
     desc.ln2_g = pk.add_f32(sd[f"{prefix}.norm2.weight"]); desc.ln2_b = pk.add_f32(sd[f"{prefix}.norm2.bias"])
-    desc.qkv_b = pk.add_f32(sd[f"{prefix}.attn.qkv.bias"]); desc.proj_b = pk.add_f32(sd[f"{prefix}.attn.proj.bias"])
+    desc.qkv_b = pk.add_f32(_pad_heads(sd[f"{prefix}.attn.qkv.bias"], heads)); desc.proj_b = pk.add_f32(sd[f"{prefix}.attn.proj.bias"])
     desc.fc1_b = pk.add_f32(sd[f"{prefix}.mlp.fc1.bias"]); desc.fc2_b = pk.add_f32(sd[f"{prefix}.mlp.fc2.bias"])
-    desc.qkv_w = pk.add_mat(sd[f"{prefix}.attn.qkv.weight"]); desc.proj_w = pk.add_mat(sd[f"{prefix}.attn.proj.weight"])
+    desc.qkv_w = pk.add_mat(_pad_heads(sd[f"{prefix}.attn.qkv.weight"], heads)); desc.proj_w = pk.add_mat(sd[f"{prefix}.attn.proj.weight"])
     desc.fc1_w = pk.add_mat(sd[f"{prefix}.mlp.fc1.weight"]); desc.fc2_w = pk.add_mat(sd[f"{prefix}.mlp.fc2.weight"])
 
 
@@ -99,7 +112,7 @@ class VitEngine:
         d.norm_g = pk.add_f32(sd["norm.weight"]); d.norm_b = pk.add_f32(sd["norm.bias"])
         d.head_w = pk.add_f32(sd["head.weight"]); d.head_b = pk.add_f32(sd["head.bias"])
         for i in range(s.depth):
-            _pack_block(pk, sd, f"blocks.{i}", d.blocks[i])
+            _pack_block(pk, sd, f"blocks.{i}", d.blocks[i], s.heads)
         self.wf32, self.wsplit, d.split_plane = pk.finish(self.device)
         self.desc = d
 
@@ -159,9 +172,9 @@ class MaeEngine:
         d.dec_norm_g = pk.add_f32(sd["decoder_norm.weight"]); d.dec_norm_b = pk.add_f32(sd["decoder_norm.bias"])
         d.pred_w = pk.add_mat(sd["decoder_pred.weight"]); d.pred_b = pk.add_f32(sd["decoder_pred.bias"])
         for i in range(s.enc_depth):
-            _pack_block(pk, sd, f"blocks.{i}", d.enc_blocks[i])
+            _pack_block(pk, sd, f"blocks.{i}", d.enc_blocks[i], s.enc_heads)
         for i in range(s.dec_depth):
-            _pack_block(pk, sd, f"decoder_blocks.{i}", d.dec_blocks[i])
+            _pack_block(pk, sd, f"decoder_blocks.{i}", d.dec_blocks[i], s.dec_heads)
         self.wf32, self.wsplit, d.split_plane = pk.finish(self.device)
         self.desc = d
 

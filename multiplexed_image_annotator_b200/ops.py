@@ -18,7 +18,7 @@ PATCH = 40
 MAX_PANEL_CH = 16
 GAUSS_STRIDE = 16
 PRECISION = {"bf16x3": 0, "bf16": 1, "bf16x1": 1, "simt": 2, "fp32": 2}
-EPI_STORE, EPI_RESIDUAL, EPI_GELU = 0, 1, 2
+EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_STORE_SPLIT = 0, 1, 2, 3
 _DTYPES = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2, torch.int32: 3}
 
 
@@ -236,7 +236,7 @@ def gemm(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None
     assert k == k2
     dev = a_split.device
     out_f32 = out_split = None
-    if epilogue == EPI_GELU:
+    if epilogue in (EPI_GELU, EPI_STORE_SPLIT):
         out_split = out if out is not None else torch.empty((2, m, n), dtype=torch.bfloat16, device=dev)
     else:
         out_f32 = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=dev)
@@ -244,7 +244,7 @@ def gemm(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None
     _lib.check(_lib.lib().ribca_gemm_splitbf16(_ptr(a_split), m * k, _ptr(w_split), n * k, m, n, k, _ptr(bias), _ptr(row_table),
                                                period, epilogue, _ptr(out_f32), _ptr(out_split), m * n, PRECISION[precision],
                                                _stream()), "ribca_gemm_splitbf16")
-    return out_split if epilogue == EPI_GELU else out_f32
+    return out_split if epilogue in (EPI_GELU, EPI_STORE_SPLIT) else out_f32
 
 
 def layernorm_split(x: torch.Tensor, gamma, beta, eps=1e-6) -> torch.Tensor:
@@ -263,6 +263,17 @@ def attention(qkv: torch.Tensor, cells: int, tokens: int, heads: int) -> torch.T
     out = torch.empty((2, m, d), dtype=torch.bfloat16, device=qkv.device)
     _lib.check(_lib.lib().ribca_attention(_ptr(qkv), cells, tokens, heads, d // heads, _ptr(out), m * d, _stream()),
                "ribca_attention")
+    return out
+
+
+def attention_tc(qkv_split: torch.Tensor, cells: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
+    """Tensor-core attention: qkv_split (2, M, 3*heads*hdp) bf16 planes -> (2, M, heads*head_dim)."""
+    _need_cuda(qkv_split)
+    _, m, wq = qkv_split.shape
+    d = heads * head_dim
+    out = torch.empty((2, m, d), dtype=torch.bfloat16, device=qkv_split.device)
+    _lib.check(_lib.lib().ribca_attention_tc(_ptr(qkv_split), m * wq, cells, tokens, heads, head_dim, _ptr(out), m * d,
+                                             _stream()), "ribca_attention_tc")
     return out
 
 

@@ -107,6 +107,25 @@ def test_layernorm_and_attention_vs_torch():
         assert err < 2e-5
 
 
+@pytest.mark.parametrize("cells,tokens,heads,hd", [(3, 101, 12, 48), (2, 101, 12, 12), (4, 101, 12, 24), (2, 101, 12, 32),
+                                                   (3, 101, 12, 64), (2, 40, 4, 16), (1, 128, 2, 64), (5, 113, 3, 48)])
+def test_attention_tensor_core_vs_torch(cells, tokens, heads, hd):
+    g = torch.Generator(device=DEV).manual_seed(cells * 1000 + tokens + hd)
+    m, hdp = cells * tokens, (hd + 15) // 16 * 16
+    qkv = torch.randn((m, 3, heads, hd), generator=g, device=DEV) * 1.5
+    padded = torch.zeros((m, 3, heads, hdp), device=DEV)
+    padded[..., :hd] = qkv
+    qs = ops.split_bf16(padded.reshape(m, 3 * heads * hdp))
+    exact = _unsplit(qs).reshape(m, 3, heads, hdp)[..., :hd]           # what the kernel really sees
+    q, k, v = exact.view(cells, tokens, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    want = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(m, heads * hd)
+    got = _unsplit(ops.attention_tc(qs, cells, tokens, heads, hd))
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item()
+    print(f"attention_tc cells={cells} tokens={tokens} heads={heads} hd={hd}: max|err|={err:.3e} |ref|max={want.abs().max().item():.2f}")
+    assert err < 5e-5
+
+
 def _vit_pair(panel, seed=1):
     sd = weights.random_vit_state(panel, seed=seed)
     ref = orc.make_vit(panel)

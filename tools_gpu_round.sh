@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out
 run() { name=$1; shift; echo "=== $name"; timeout 600 "$@" > gpurun_out/$name.log 2>&1; echo "$name exit $?" | tee -a gpurun_out/summary.txt; tail -5 gpurun_out/$name.log; }
 : > gpurun_out/summary.txt
 run stages python -m pytest tests/test_gpu_stages.py -q -m gpu --timeout 300 -p no:cacheprovider
-run gemm python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "gemm or layernorm"
+run gemm python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "gemm or layernorm or attention"
 run networks python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "vit or mae"
 run e2e python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "annotator"
 run smoke python __graft_entry__.py smoke
