@@ -123,7 +123,8 @@ def test_attention_tensor_core_vs_torch(cells, tokens, heads, hd):
     torch.cuda.synchronize()
     err = (got - want).abs().max().item()
     print(f"attention_tc cells={cells} tokens={tokens} heads={heads} hd={hd}: max|err|={err:.3e} |ref|max={want.abs().max().item():.2f}")
-    assert err < 5e-5
+    # the output itself is quantised to split-bf16 (16 mantissa bits): 2^-16 of its magnitude
+    assert err < 2.0 ** -16 * max(1.0, want.abs().max().item()) * 1.5
 
 
 def _vit_pair(panel, seed=1):
