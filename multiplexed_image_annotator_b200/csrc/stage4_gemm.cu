@@ -15,7 +15,7 @@
 //     warp 1     allocates 512 TMEM columns, one lane issues tcgen05.mma (M=128, N=BN<=256, K=16)
 //                from shared-memory descriptors; tcgen05.commit releases ring slots / publishes
 //                the accumulator
-//     warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias / row table / residual / GELU
+//     warps 2-9  epilogue (two warps per TMEM lane quadrant, alternating 16-column chunks): tcgen05.ld (32 lanes x 16 columns) -> bias / row table / residual / GELU
 //                -> global; TMEM is double-buffered (2 x 256 columns) so the epilogue of tile t
 //                overlaps the main loop of tile t+1
 //   tiles are ordered m-major so the CTAs of one wave share A rows through L2 and W stays L2-resident.
@@ -29,7 +29,8 @@ constexpr int BK = 64;              // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
 constexpr int kMaxBN = 256;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant, interleaved over 16-column chunks
+constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr int kABytes = BM * BK * 2;            // 16 KB
 constexpr int kBBytesMax = kMaxBN * BK * 2;     // 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
@@ -83,7 +84,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -140,24 +141,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                      // which of the two warps of the quadrant
     int local = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t use = (uint32_t)(local >> 1);
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
-      mbar_wait(&tmem_full[buf], use & 1u);
-      tcgen05_fence_after();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < shp.M;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
       const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
-      for (int c = 0; c < BN; c += 16) {
+      const long long row_off = (long long)row * shp.N;
+      const bool residual = epi.mode == RIBCA_EPI_RESIDUAL;
+      // residual: the x tile does not depend on the accumulator, so fetch the first chunk before waiting
+      float4 xr[4];
+      if (residual && row_ok) {
+        const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + n0 + half * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xr[q] = px[q];
+      }
+      mbar_wait(&tmem_full[buf], use & 1u);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
+      for (int c = half * 16; c < BN; c += 32) {
         float v[16];
         tmem_ld16(t_row + (uint32_t)c, v);
         if (row_ok) {
           const int col = n0 + c;
+          if (residual) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { v[4 * q] += xr[q].x; v[4 * q + 1] += xr[q].y; v[4 * q + 2] += xr[q].z; v[4 * q + 3] += xr[q].w; }
+            if (c + 32 < BN) {                             // prefetch the next chunk's x under this chunk's math
+              const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + col + 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) xr[q] = px[q];
+            }
+          }
           if (epi.bias) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -172,7 +192,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
             }
           }
-          const long long o = (long long)row * shp.N + col;
+          const long long o = row_off + col;
           if (epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT) {
             __align__(16) __nv_bfloat16 hi[16], lo[16];
             if (epi.mode == RIBCA_EPI_GELU) {
@@ -187,13 +207,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             pl[0] = reinterpret_cast<const uint4*>(lo)[0]; pl[1] = reinterpret_cast<const uint4*>(lo)[1];
           } else {
             float4* po = reinterpret_cast<float4*>(epi.out_f32 + o);
-            if (epi.mode == RIBCA_EPI_RESIDUAL) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 x = po[q];
-                v[4 * q] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
-              }
-            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
