@@ -4,14 +4,16 @@
 // cta/markerImputer.py:186-232).  A single bf16 pass cannot hold the 1e-3 probability tolerance
 // (SURVEY section 7), so operands are stored as two bf16 planes x = hi + lo and the product is
 // accumulated in fp32 TMEM as  lo.hi + hi.lo + hi.hi  (three tcgen05 passes over K, "bf16x3").
-// Because the split is a data layout, the kernel itself is a plain K-major bf16 GEMM whose K loop
-// walks a list of (A plane, W plane) pairs; bf16x1 just walks one pair.
+// Because the split is a data layout, the kernel is a plain K-major bf16 GEMM: every K block stages
+// the four tiles {A_hi, A_lo, W_hi, W_lo} ONCE (two TMA boxes of depth 2 over the plane axis) and
+// issues the three products from them, so the operands cross L2 -> shared memory once, not three
+// times (131 FLOP per staged byte at BN = 256); bf16x1 stages and multiplies the hi planes only.
 //
 // Kernel shape (sm_100a, cta_group::1):
 //   persistent grid, one CTA per SM, 192 threads = 6 warps
-//     warp 0     TMA producer: 3-D tensor maps (K, rows, plane), 128B swizzle, box 64 x rows x 1,
+//     warp 0     TMA producer: 3-D tensor maps (K, rows, plane), 64B swizzle, box 32 x rows x planes,
 //                4-stage shared ring, mbarrier expect_tx; out-of-range K / rows are zero-filled by
-//                the TMA unit, so K need not be a multiple of 64 nor M of 128
+//                the TMA unit, so K need not be a multiple of 32 nor M of 128
 //     warp 1     allocates 512 TMEM columns, one lane issues tcgen05.mma (M=128, N=BN<=256, K=16)
 //                from shared-memory descriptors; tcgen05.commit releases ring slots / publishes
 //                the accumulator
@@ -25,14 +27,15 @@
 namespace ribca {
 
 constexpr int BM = 128;
-constexpr int BK = 64;              // 64 bf16 = 128 bytes = one swizzle row
+constexpr int BK = 32;              // 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
 constexpr int kMaxBN = 256;
 constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant, interleaved over 16-column chunks
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
-constexpr int kABytes = BM * BK * 2;            // 16 KB
-constexpr int kBBytesMax = kMaxBN * BK * 2;     // 32 KB
+constexpr int kATile = BM * BK * 2;             // one plane of A:  8 KB
+constexpr int kABytes = 2 * kATile;             // hi + lo:        16 KB
+constexpr int kBBytesMax = 2 * kMaxBN * BK * 2; // W hi + lo:      32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
@@ -50,9 +53,7 @@ struct GemmEpilogue {
 struct GemmShape {
   int M, N, K;
   int BN;                   // N tile (multiple of 16, <= 256, divides N)
-  int n_pass;               // 3 (bf16x3) or 1
-  int a_plane[3];           // plane index of A per pass
-  int w_plane[3];
+  int n_planes;             // 2 (bf16x3: hi and lo staged) or 1 (bf16x1: hi only)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -77,8 +78,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int n_tiles_m = (shp.M + BM - 1) / BM;
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int n_kb = (shp.K + BK - 1) / BK;
-  const int n_iter = n_kb * shp.n_pass;
-  const uint32_t stage_tx = (uint32_t)(kABytes + BN * BK * 2);
+  const int n_iter = n_kb;
+  const int w_tile = BN * BK * 2;                        // one plane of the W tile
+  const uint32_t stage_tx = (uint32_t)(shp.n_planes * (kATile + w_tile));
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -99,14 +101,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
-        for (int it = 0; it < n_iter; ++it) {
-          const int pass = it / n_kb, kb = it - pass * n_kb;
+        for (int kb = 0; kb < n_iter; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[stage], stage_tx);
-          tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, shp.a_plane[pass]);
-          tma_load_3d(sb, &tmap_w, &full_bar[stage], kb * BK, n0, shp.w_plane[pass]);
+          tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, 0);      // box depth = n_planes: hi tile, then lo tile
+          tma_load_3d(sb, &tmap_w, &full_bar[stage], kb * BK, n0, 0);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -128,11 +129,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
+          if (shp.n_planes == 2) {
+            // lo.hi + hi.lo + hi.hi from the four staged tiles
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
-            const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
-            umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t a_hi = make_smem_desc_sw64(a_addr + k * UMMA_K * 2);
+              const uint64_t a_lo = make_smem_desc_sw64(a_addr + kATile + k * UMMA_K * 2);
+              const uint64_t w_hi = make_smem_desc_sw64(b_addr + k * UMMA_K * 2);
+              const uint64_t w_lo = make_smem_desc_sw64(b_addr + w_tile + k * UMMA_K * 2);
+              umma_bf16(d_tmem, a_lo, w_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, a_hi, w_lo, idesc, 1u);
+              umma_bf16(d_tmem, a_hi, w_hi, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d_tmem, make_smem_desc_sw64(a_addr + k * UMMA_K * 2), make_smem_desc_sw64(b_addr + k * UMMA_K * 2),
+                        idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                  // slot reusable once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -154,28 +167,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
       const long long row_off = (long long)row * shp.N;
       const bool residual = epi.mode == RIBCA_EPI_RESIDUAL;
-      // residual: the x tile does not depend on the accumulator, so fetch the first chunk before waiting
-      float4 xr[4];
+      // residual: the x tile does not depend on the accumulator: keep up to kPref chunks (64 B each) of it
+      // in flight per thread, the first ones fetched before the accumulator is even complete
+      constexpr int kPref = 4;
+      float4 xr[kPref][4];
+      const int n_mine = (BN / 16 - half + 1) / 2;         // chunks this warp handles: half, half+2, ...
       if (residual && row_ok) {
-        const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + n0 + half * 16);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xr[q] = px[q];
+        for (int u = 0; u < kPref; ++u) {
+          if (u < n_mine) {
+            const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + n0 + (half + 2 * u) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xr[u][q] = px[q];
+          }
+        }
       }
       mbar_wait(&tmem_full[buf], use & 1u);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
-      for (int c = half * 16; c < BN; c += 32) {
+      for (int j0 = 0; j0 < n_mine; j0 += kPref) {
+#pragma unroll
+       for (int u = 0; u < kPref; ++u) {
+        const int j = j0 + u;
+        if (j >= n_mine) break;
+        const int c = (half + 2 * j) * 16;
         float v[16];
         tmem_ld16(t_row + (uint32_t)c, v);
         if (row_ok) {
           const int col = n0 + c;
           if (residual) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { v[4 * q] += xr[q].x; v[4 * q + 1] += xr[q].y; v[4 * q + 2] += xr[q].z; v[4 * q + 3] += xr[q].w; }
-            if (c + 32 < BN) {                             // prefetch the next chunk's x under this chunk's math
-              const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + col + 32);
+            for (int q = 0; q < 4; ++q) { v[4 * q] += xr[u][q].x; v[4 * q + 1] += xr[u][q].y; v[4 * q + 2] += xr[u][q].z; v[4 * q + 3] += xr[u][q].w; }
+            if (j + kPref < n_mine) {                      // refill this ring slot
+              const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + col + 2 * kPref * 16);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) xr[q] = px[q];
+              for (int q = 0; q < 4; ++q) xr[u][q] = px[q];
             }
           }
           if (epi.bias) {
@@ -211,6 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int q = 0; q < 4; ++q) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
+       }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -299,16 +326,17 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n, __nv
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// 3-D map over a split operand: dims (K, rows, 2 planes), box (64, box_rows, 1), 128B swizzle
-static int make_operand_map(CUtensorMap* map, const void* base, long long plane_elems, int rows, int K, int box_rows) {
+// 3-D map over a split operand: dims (K, rows, 2 planes), box (32, box_rows, n_planes), 64B swizzle
+static int make_operand_map(CUtensorMap* map, const void* base, long long plane_elems, int rows, int K, int box_rows,
+                            int n_planes) {
   auto encode = tensor_map_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return RIBCA_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_elems * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)n_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d box_rows=%d plane=%lld", (int)r, rows, K, box_rows, plane_elems);
@@ -340,14 +368,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   shp.M = M; shp.N = N; shp.K = K;
   shp.BN = pick_bn(N);
   RIBCA_REQUIRE(shp.BN > 0, "gemm: no N tile for N=%d", N);
-  if (precision == RIBCA_BF16X1) {
-    shp.n_pass = 1; shp.a_plane[0] = 0; shp.w_plane[0] = 0;
-  } else {
-    shp.n_pass = 3;                       // small terms first, then hi.hi
-    shp.a_plane[0] = 1; shp.w_plane[0] = 0;
-    shp.a_plane[1] = 0; shp.w_plane[1] = 1;
-    shp.a_plane[2] = 0; shp.w_plane[2] = 0;
-  }
+  shp.n_planes = precision == RIBCA_BF16X1 ? 1 : 2;
   GemmEpilogue epi;
   epi.bias = bias; epi.row_table = row_table; epi.table_period = table_period > 0 ? table_period : 1;
   epi.mode = epilogue; epi.out_f32 = out_f32;
@@ -363,8 +384,8 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   }
   RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1, "gemm: unknown precision %d", precision);
   CUtensorMap map_a, map_w;
-  RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM));
-  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN));
+  RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
+  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN, shp.n_planes));
   static bool attr_set = false;
   if (!attr_set) {
     RIBCA_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
