@@ -17,9 +17,12 @@
 //     warp 1     allocates 512 TMEM columns, one lane issues tcgen05.mma (M=128, N=BN<=256, K=16)
 //                from shared-memory descriptors; tcgen05.commit releases ring slots / publishes
 //                the accumulator
-//     warps 2-9  epilogue (two warps per TMEM lane quadrant, alternating 16-column chunks): tcgen05.ld (32 lanes x 16 columns) -> bias / row table / residual / GELU
-//                -> global; TMEM is double-buffered (2 x 256 columns) so the epilogue of tile t
-//                overlaps the main loop of tile t+1
+//     warps 2-9  epilogue (two warps per TMEM lane quadrant, alternating column chunks): tcgen05.ld ->
+//                bias / row table / GELU / split -> swizzled shared staging -> TMA bulk tensor store
+//                (full cache lines, no LSU serialisation); the residual add is a TMA reduce-add
+//                (cp.reduce.async.bulk.tensor .add.f32), so x is never read into the SM.
+//                TMEM is double-buffered (2 x 256 columns): the epilogue of tile t overlaps the main
+//                loop of tile t+1
 //   tiles are ordered m-major so the CTAs of one wave share A rows through L2 and W stays L2-resident.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -30,14 +33,15 @@ constexpr int BM = 128;
 constexpr int BK = 32;              // 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
+constexpr int kEpiWarps = 8;        // two per TMEM lane quadrant, alternating column chunks
 constexpr int kMaxBN = 256;
-constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant, interleaved over 16-column chunks
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr int kATile = BM * BK * 2;             // one plane of A:  8 KB
 constexpr int kABytes = 2 * kATile;             // hi + lo:        16 KB
 constexpr int kBBytesMax = 2 * kMaxBN * BK * 2; // W hi + lo:      32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStagingBytes = 4096;           // per epilogue warp: 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo)
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
 
 struct GemmEpilogue {
@@ -45,8 +49,9 @@ struct GemmEpilogue {
   const float* row_table;   // [table_period][N] or null
   int table_period;
   int mode;                 // ribca_epilogue
-  float* out_f32;           // [M][N]
-  __nv_bfloat16* out_hi;    // split output planes (GELU mode)
+  int chunk;                // columns per staged TMA store: 32, or 16 when BN % 32 != 0
+  float* out_f32;           // [M][N]          (SIMT path only; the tcgen05 path stores through tmap_out)
+  __nv_bfloat16* out_hi;    // split output planes
   __nv_bfloat16* out_lo;
 };
 
@@ -59,12 +64,112 @@ struct GemmShape {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ---------------------------------------------------------------------------------------------
+// ---- epilogue: TMEM -> registers -> swizzled staging -> TMA store / reduce-add -----------------------
+// CW columns per step.  fp32 outputs: staging rows of CW*4 bytes (128B swizzle for CW = 32, 64B for 16);
+// split outputs: hi tile then lo tile, rows of CW*2 bytes (64B swizzle for CW = 32, 32B for 16).
+template <int CW>
+__device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const GemmShape& shp, const GemmEpilogue& epi,
+                                              uint8_t* staging_base, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, int warp, int lane) {
+  const int BN = shp.BN;
+  const int n_tiles_n = shp.N / BN;
+  const int n_tiles = ((shp.M + BM - 1) / BM) * n_tiles_n;
+  const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
+  const int half = (warp - 2) >> 2;                      // which of the two warps of the quadrant
+  uint8_t* stg = staging_base + (warp - 2) * kStagingBytes;
+  const uint32_t stg_addr = smem_u32(stg);
+  const bool split_out = epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT;
+  const int n_chunks = BN / CW;
+  int local = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+    const int buf = local & 1;
+    const uint32_t use = (uint32_t)(local >> 1);
+    const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+    const int row = m0 + quad * 32 + lane;
+    const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
+    mbar_wait(&tmem_full[buf], use & 1u);
+    tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
+    for (int j = half; j < n_chunks; j += 2) {
+      const int c = j * CW;
+      const int col = n0 + c;
+      float v[CW];
+#pragma unroll
+      for (int q = 0; q < CW / 16; ++q) tmem_ld16(t_row + (uint32_t)(c + 16 * q), v + 16 * q);
+      if (epi.bias) {
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q);
+          v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+        }
+      }
+      if (table_row) {
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(table_row + col) + q);
+          v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+        }
+      }
+      // the previous bulk store of this warp must have finished READING the staging tile
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (split_out) {
+        if (epi.mode == RIBCA_EPI_GELU) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = gelu_erf(v[i]);
+        }
+        // rows of CW bf16 (CW*2 bytes); 16-byte chunk index XOR-swizzled like the TMA store expects
+        constexpr int kRowB = CW * 2, kChunks = kRowB / 16;
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_bf16(v[ch * 8 + e], hi[e], lo[e]);
+          const int sw = (CW == 32) ? (ch ^ ((lane >> 1) & 3)) : (ch ^ ((lane >> 2) & 1));   // SWIZZLE_64B / SWIZZLE_32B
+          const int off = lane * kRowB + (sw << 4);
+          *reinterpret_cast<uint4*>(stg + off) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(stg + 32 * kRowB + off) = *reinterpret_cast<const uint4*>(lo);
+        }
+      } else {
+        constexpr int kRowB = CW * 4, kChunks = kRowB / 16;
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int sw = (CW == 32) ? (ch ^ (lane & 7)) : (ch ^ ((lane >> 1) & 3));           // SWIZZLE_128B / SWIZZLE_64B
+          *reinterpret_cast<float4*>(stg + lane * kRowB + (sw << 4)) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int r0 = m0 + quad * 32;
+        if (split_out) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(stg_addr), "r"(col), "r"(r0), "r"(0) : "memory");
+        } else if (epi.mode == RIBCA_EPI_RESIDUAL) {
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(stg_addr), "r"(col), "r"(r0) : "memory");
+        } else {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(stg_addr), "r"(col), "r"(r0) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores of this warp have landed
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const GemmShape shp, const GemmEpilogue epi) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmShape shp, const GemmEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging_base = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + kEpiWarps * kStagingBytes);
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
@@ -85,6 +190,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_out);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpiWarps); }
     fence_barrier_init();
@@ -155,94 +261,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
-    const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;                      // which of the two warps of the quadrant
-    int local = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
-      const int buf = local & 1;
-      const uint32_t use = (uint32_t)(local >> 1);
-      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < shp.M;
-      const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
-      const long long row_off = (long long)row * shp.N;
-      const bool residual = epi.mode == RIBCA_EPI_RESIDUAL;
-      // residual: the x tile does not depend on the accumulator: keep up to kPref chunks (64 B each) of it
-      // in flight per thread, the first ones fetched before the accumulator is even complete
-      constexpr int kPref = 4;
-      float4 xr[kPref][4];
-      const int n_mine = (BN / 16 - half + 1) / 2;         // chunks this warp handles: half, half+2, ...
-      if (residual && row_ok) {
-#pragma unroll
-        for (int u = 0; u < kPref; ++u) {
-          if (u < n_mine) {
-            const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + n0 + (half + 2 * u) * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) xr[u][q] = px[q];
-          }
-        }
-      }
-      mbar_wait(&tmem_full[buf], use & 1u);
-      tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
-      for (int j0 = 0; j0 < n_mine; j0 += kPref) {
-#pragma unroll
-       for (int u = 0; u < kPref; ++u) {
-        const int j = j0 + u;
-        if (j >= n_mine) break;
-        const int c = (half + 2 * j) * 16;
-        float v[16];
-        tmem_ld16(t_row + (uint32_t)c, v);
-        if (row_ok) {
-          const int col = n0 + c;
-          if (residual) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { v[4 * q] += xr[u][q].x; v[4 * q + 1] += xr[u][q].y; v[4 * q + 2] += xr[u][q].z; v[4 * q + 3] += xr[u][q].w; }
-            if (j + kPref < n_mine) {                      // refill this ring slot
-              const float4* px = reinterpret_cast<const float4*>(epi.out_f32 + row_off + col + 2 * kPref * 16);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) xr[u][q] = px[q];
-            }
-          }
-          if (epi.bias) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q);
-              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-            }
-          }
-          if (table_row) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(table_row + col) + q);
-              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-            }
-          }
-          const long long o = row_off + col;
-          if (epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT) {
-            __align__(16) __nv_bfloat16 hi[16], lo[16];
-            if (epi.mode == RIBCA_EPI_GELU) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) split_bf16(v[i], hi[i], lo[i]);
-            uint4* ph = reinterpret_cast<uint4*>(epi.out_hi + o);
-            uint4* pl = reinterpret_cast<uint4*>(epi.out_lo + o);
-            ph[0] = reinterpret_cast<const uint4*>(hi)[0]; ph[1] = reinterpret_cast<const uint4*>(hi)[1];
-            pl[0] = reinterpret_cast<const uint4*>(lo)[0]; pl[1] = reinterpret_cast<const uint4*>(lo)[1];
-          } else {
-            float4* po = reinterpret_cast<float4*>(epi.out_f32 + o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
-        }
-       }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-    }
+    if (epi.chunk == 32) epilogue_loop<32>(tmap_out, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
+    else                 epilogue_loop<16>(tmap_out, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -345,6 +365,31 @@ static int make_operand_map(CUtensorMap* map, const void* base, long long plane_
   return RIBCA_OK;
 }
 
+// tensor map of the output: fp32 [M][N] (2-D) or split-bf16 planes [2][M][N] (3-D, both planes per store)
+static int make_output_map(CUtensorMap* map, bool split, void* base, long long plane_elems, int M, int N, int chunk) {
+  auto encode = tensor_map_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return RIBCA_ECUDA; }
+  CUresult r;
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (split) {
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)plane_elems * 2};
+    cuuint32_t box[3] = {(cuuint32_t)chunk, 32, 2};
+    r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               chunk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+    cuuint32_t box[2] = {(cuuint32_t)chunk, 32};
+    r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               chunk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed (%d) M=%d N=%d chunk=%d", (int)r, M, N, chunk); return RIBCA_ECUDA; }
+  return RIBCA_OK;
+}
+
 int pick_bn(int N) {
   for (int bn = kMaxBN; bn >= 16; bn -= 16)
     if (N % bn == 0) return bn;
@@ -371,7 +416,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   shp.n_planes = precision == RIBCA_BF16X1 ? 1 : 2;
   GemmEpilogue epi;
   epi.bias = bias; epi.row_table = row_table; epi.table_period = table_period > 0 ? table_period : 1;
-  epi.mode = epilogue; epi.out_f32 = out_f32;
+  epi.mode = epilogue; epi.out_f32 = out_f32; epi.chunk = 32;
   epi.out_hi = static_cast<__nv_bfloat16*>(out_split);
   epi.out_lo = out_split ? static_cast<__nv_bfloat16*>(out_split) + out_plane : nullptr;
 
@@ -383,9 +428,12 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
     return RIBCA_OK;
   }
   RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1, "gemm: unknown precision %d", precision);
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_out;
   RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
   RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN, shp.n_planes));
+  epi.chunk = shp.BN % 32 == 0 ? 32 : 16;
+  RIBCA_REQUIRE(!split_out || (out_plane * 2) % 16 == 0, "gemm: split output plane stride must be 16-byte aligned");
+  RIBCA_TRY(make_output_map(&map_out, split_out, split_out ? out_split : (void*)out_f32, out_plane, M, N, epi.chunk));
   static bool attr_set = false;
   if (!attr_set) {
     RIBCA_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
@@ -396,7 +444,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   const int grid = std::min(n_tiles, num_sms());
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream);
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, shp, epi);
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, map_out, shp, epi);
   if (prof) prof_end_span(stream);
   RIBCA_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return RIBCA_OK;
