@@ -3,17 +3,19 @@
 //
 // Input: the QKV GEMM's output in split-bf16 planes [2][M][3 * heads * hdp] (hdp = head_dim rounded up
 // to 16, padding columns are exact zeros because the padded weight rows are zero).
-// One persistent CTA (128 threads) per SM keeps two (cell, head) items in flight; per item:
+// One persistent CTA per SM with two independent warpgroups; each warpgroup streams (cell, head) items
+// through its own shared-memory slot, TMEM columns and mbarriers:
 //   1. TMA: Q (128 rows), K and V (TP rows) of the head, hi and lo planes, 128B-swizzled 64-column boxes
-//   2. S = Q K^T  : tcgen05.mma M=128, N=TP, K=hdp, three split passes (lo.hi + hi.lo + hi.hi) into TMEM
-//   3. softmax    : thread r owns row r: tcgen05.ld -> scale, mask columns >= tokens, max, exp, sum;
-//                   P is written back to shared memory as split-bf16 in the K-major swizzled layout
-//                   (over the dead Q / K tiles)
-//   4. O = P V    : tcgen05.mma M=128, N=hdp, K=TP; V is consumed as an MN-major B operand straight
-//                   from its TMA tile (token rows, head_dim contiguous); three split passes
+//   2. S = Q K^T  : tcgen05.mma M=128, N=TP, K=hdp, three split passes (lo.hi + hi.lo + hi.hi) into TMEM;
+//                   as soon as it retires the next item's Q / K are prefetched into the same tiles
+//   3. softmax    : thread r owns row r: tcgen05.ld -> max, ex2(scale*log2e*(s - max)), sum; P is packed
+//                   to split bf16x2 and written back INTO TMEM over S (tcgen05.st), so it never touches
+//                   shared memory
+//   4. O = P V    : tcgen05.mma with A = P from TMEM and V as an MN-major B operand straight from its TMA
+//                   tile (token rows, head_dim contiguous); three split passes; V is then prefetched
 //   5. O / rowsum -> split-bf16 [2][M][D] (the next GEMM's A operand)
-// Rows / columns beyond `tokens` inside the 128 x TP tile hold the next cell's tokens (or TMA zero
-// fill); they are masked in the softmax and never stored.
+// While one warpgroup waits on its MMAs the other runs its softmax.  Rows / columns beyond `tokens`
+// inside the 128 x TP tile hold the next cell's tokens (or TMA zero fill); they are masked and never stored.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -21,14 +23,14 @@ namespace ribca {
 
 typedef __nv_bfloat16 bf16;
 
-constexpr int kAttThreads = 128;
+constexpr int kAttThreads = 256;
 constexpr int kQBytes = 128 * 128;            // 128 rows x 64 bf16
-constexpr int kSlotBytes = 65536 + 2 * 128 * 128;                  // Q/K (later P) region + V tiles, sized for TP = 128
-constexpr int kAttSmemBytes = 2 * kSlotBytes + 1024 + 128;         // two items in flight + align + barriers
+constexpr int kSlotBytes = 6 * 128 * 128;     // Q, K, V x {hi, lo}, sized for TP = 128 (96 KB)
+constexpr int kAttSmemBytes = 2 * kSlotBytes + 1024 + 128;
 
 struct AttnParams {
   int cells, tokens, heads, hd, hdp, D;
-  float scale;
+  float scale_log2e;                          // log2(e) / sqrt(head_dim)
 };
 
 // MN-major (N contiguous) B operand in a 128B-swizzled tile whose rows are K indices:
@@ -42,10 +44,34 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+// D[tmem] (+)= A[tmem] . B[smem]: A rows are TMEM lanes, each 32-bit column holds two consecutive K elements
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (a, b) -> packed split bf16x2: hi = bf16x2(a, b), lo = bf16x2(a - hi.a, b - hi.b); element a in the low half
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
-// Two (cell, head) items are in flight per CTA (slots 0 / 1), each with its own shared tiles, TMEM
-// accumulators and mbarriers, so the TMA loads and the MMAs of one slot run under the softmax of the other:
-//   S0, S1 issued | softmax 0 -> PV0 issued | softmax 1 -> PV1 issued | O0 out, reload slot 0 | O1 out, reload slot 1
 template <int TP>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -54,13 +80,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSlotBytes);
-  uint64_t* bar_qk = bars;          // [2] TMA  -> S MMA
-  uint64_t* bar_v = bars + 2;       // [2] TMA  -> PV MMA
-  uint64_t* bar_s = bars + 4;       // [2] S done  -> softmax
-  uint64_t* bar_o = bars + 6;       // [2] PV done -> output, slot reload
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7;                   // warpgroup = slot
+  const int row = tid & 127;                 // query row owned by this thread
+  const bool leader = row == 0;
+  uint64_t* bar_qk = bars + 4 * wg;          // TMA  -> S MMA
+  uint64_t* bar_v = bar_qk + 1;              // TMA  -> PV MMA
+  uint64_t* bar_s = bar_qk + 2;              // S done  -> softmax, Q / K reload
+  uint64_t* bar_o = bar_qk + 3;              // PV done -> output, V reload
   if (tid == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_kv);
@@ -72,164 +101,140 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+  const uint32_t tmem_sp = tmem_base + wg * 256;           // S (fp32, TP cols); later P_hi at +0, P_lo at +64 (bf16x2)
+  const uint32_t tmem_o = tmem_base + wg * 256 + 128;      // O (fp32, hdp cols)
+
+  uint8_t* slot = smem + wg * kSlotBytes;
+  uint8_t* q_s[2] = {slot, slot + kQBytes};
+  uint8_t* k_s[2] = {slot + 2 * kQBytes, slot + 2 * kQBytes + kKVBytes};
+  uint8_t* v_s[2] = {slot + 4 * kQBytes, slot + 4 * kQBytes + kKVBytes};
 
   const uint32_t idesc_s = make_instr_desc(128, TP, false);
   const uint32_t idesc_o = make_instr_desc(128, p.hdp, true);
   const int ksteps_s = p.hdp / 16;
   const int n_items = p.cells * p.heads;
-  const int my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int first = blockIdx.x * 2 + wg, stride = 2 * gridDim.x;
+  const int my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
 
-  auto slot_q = [&](int sl, int pl) { return smem + sl * kSlotBytes + pl * kQBytes; };
-  auto slot_k = [&](int sl, int pl) { return smem + sl * kSlotBytes + 2 * kQBytes + pl * kKVBytes; };
-  auto slot_p = [&](int sl, int pl) { return smem + sl * kSlotBytes + pl * 32768; };      // overlays Q / K
-  auto slot_v = [&](int sl, int pl) { return smem + sl * kSlotBytes + 65536 + pl * kKVBytes; };
-  auto item_of = [&](int k) { return blockIdx.x + k * (int)gridDim.x; };                  // k-th item of this CTA
-
-  auto issue_loads = [&](int sl, int item) {            // thread 0 only
+  auto load_qk = [&](int item) {
     const int cell = item / p.heads, head = item - cell * p.heads;
     const int row0 = cell * p.tokens;
-    const int cq = head * p.hdp, ck = (p.heads + head) * p.hdp, cv = (2 * p.heads + head) * p.hdp;
-    mbar_expect_tx(&bar_qk[sl], 2u * kQBytes + 2u * kKVBytes);
-    mbar_expect_tx(&bar_v[sl], 2u * kKVBytes);
+    mbar_expect_tx(bar_qk, 2u * kQBytes + 2u * kKVBytes);
     for (int pl = 0; pl < 2; ++pl) {
-      tma_load_3d(slot_q(sl, pl), &tmap_q, &bar_qk[sl], cq, row0, pl);
-      tma_load_3d(slot_k(sl, pl), &tmap_kv, &bar_qk[sl], ck, row0, pl);
+      tma_load_3d(q_s[pl], &tmap_q, bar_qk, head * p.hdp, row0, pl);
+      tma_load_3d(k_s[pl], &tmap_kv, bar_qk, (p.heads + head) * p.hdp, row0, pl);
     }
-    for (int pl = 0; pl < 2; ++pl) tma_load_3d(slot_v(sl, pl), &tmap_kv, &bar_v[sl], cv, row0, pl);
   };
-  auto issue_s = [&](int sl) {                           // thread 0 only: S = Q K^T, lo.hi + hi.lo + hi.hi
-    const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
-    uint32_t acc = 0;
-    for (int ps = 0; ps < 3; ++ps) {
-      const uint32_t qa = smem_u32(slot_q(sl, pa[ps])), kb = smem_u32(slot_k(sl, pb[ps]));
-      for (int ks = 0; ks < ksteps_s; ++ks) {
-        umma_bf16(tmem_base + sl * 128, make_smem_desc(qa + ks * 32), make_smem_desc(kb + ks * 32), idesc_s, acc);
-        acc = 1;
+  auto load_v = [&](int item) {
+    const int cell = item / p.heads, head = item - cell * p.heads;
+    mbar_expect_tx(bar_v, 2u * kKVBytes);
+    for (int pl = 0; pl < 2; ++pl) tma_load_3d(v_s[pl], &tmap_kv, bar_v, (2 * p.heads + head) * p.hdp, cell * p.tokens, pl);
+  };
+
+  if (leader && my_items > 0) { load_qk(first); load_v(first); }
+  uint32_t ph = 0;
+  for (int k = 0; k < my_items; ++k, ph ^= 1u) {
+    const int item = first + k * stride;
+    const int cell = item / p.heads, head = item - cell * p.heads;
+    // ---- S = Q K^T ------------------------------------------------------------------------------------
+    if (leader) {
+      mbar_wait(bar_qk, ph);
+      tcgen05_fence_after();
+      const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};       // lo.hi, hi.lo, hi.hi
+      uint32_t acc = 0;
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t qa = smem_u32(q_s[pa[ps]]), kb = smem_u32(k_s[pb[ps]]);
+        for (int ks = 0; ks < ksteps_s; ++ks) {
+          umma_bf16(tmem_sp, make_smem_desc(qa + ks * 32), make_smem_desc(kb + ks * 32), idesc_s, acc);
+          acc = 1;
+        }
       }
+      umma_commit(bar_s);
     }
-    umma_commit(&bar_s[sl]);
-  };
-  auto issue_pv = [&](int sl) {                          // thread 0 only: O = P V
-    const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
-    uint32_t acc = 0;
-    for (int ps = 0; ps < 3; ++ps) {
-      const uint32_t pa_addr = smem_u32(slot_p(sl, pa[ps])), vb = smem_u32(slot_v(sl, pb[ps]));
-#pragma unroll
-      for (int kk = 0; kk < TP / 16; ++kk) {
-        umma_bf16(tmem_base + 256 + sl * 64, make_smem_desc(pa_addr + (kk >> 2) * 16384 + (kk & 3) * 32),
-                  make_smem_desc_mn(vb + kk * 2048), idesc_o, acc);
-        acc = 1;
-      }
-    }
-    umma_commit(&bar_o[sl]);
-  };
-  // softmax of row `tid` of slot sl; P (split bf16, K-major 128B swizzle) over the dead Q / K tiles; returns the row sum
-  auto softmax_to_p = [&](int sl) -> float {
+    mbar_wait(bar_s, ph);
+    tcgen05_fence_after();
+    if (leader && k + 1 < my_items) load_qk(item + stride);     // Q / K tiles are dead: prefetch the next item
+    // ---- softmax of this thread's row; P -> TMEM over S -----------------------------------------------
     float s[TP];
 #pragma unroll
-    for (int c = 0; c < TP / 16; ++c) tmem_ld16(tmem_base + sl * 128 + lane_addr + c * 16, s + c * 16);
+    for (int c = 0; c < TP / 16; ++c) tmem_ld16(tmem_sp + lane_addr + c * 16, s + c * 16);
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < TP; ++j) {
-      s[j] = j < p.tokens ? s[j] * p.scale : -INFINITY;
+      if (j >= 96 && j >= p.tokens) s[j] = -INFINITY;         // only the tail chunk can be out of range (tokens > 96)
       mx = fmaxf(mx, s[j]);
     }
+    if (p.tokens <= 96) {                                       // generic (short sequences): mask everything
+#pragma unroll
+      for (int j = 0; j < TP; ++j) if (j >= p.tokens) s[j] = -INFINITY;
+      mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < TP; ++j) mx = fmaxf(mx, s[j]);
+    }
+    const float off = mx * p.scale_log2e;
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < TP; ++j) {
-      s[j] = expf(s[j] - mx);            // exp(-inf) = 0 for the masked columns
+      s[j] = fast_exp2(fmaf(s[j], p.scale_log2e, -off));       // exp((s - max) / sqrt(hd)); 0 for masked columns
       sum += s[j];
     }
-    uint8_t* p_hi = slot_p(sl, 0);
-    uint8_t* p_lo = slot_p(sl, 1);
-    const int r = tid;
 #pragma unroll
-    for (int ch = 0; ch < TP / 8; ++ch) {
-      __align__(16) bf16 h[8], l[8];
+    for (int c = 0; c < TP / 16; ++c) {
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) split_bf16(s[ch * 8 + e], h[e], l[e]);
-      const int off = (ch >> 3) * 16384 + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(p_hi + off) = *reinterpret_cast<const uint4*>(h);
-      *reinterpret_cast<uint4*>(p_lo + off) = *reinterpret_cast<const uint4*>(l);
+      for (int e = 0; e < 8; ++e) split_bf16x2(s[c * 16 + 2 * e], s[c * 16 + 2 * e + 1], hi[e], lo[e]);
+      tmem_st8(tmem_sp + lane_addr + c * 8, hi);
+      tmem_st8(tmem_sp + lane_addr + 64 + c * 8, lo);
     }
-    fence_proxy_async_smem();
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tcgen05_fence_before();
-    return sum;
-  };
-  auto store_o = [&](int sl, int item, float sum) {
-    const int cell = item / p.heads, head = item - cell * p.heads;
-    const float inv = 1.0f / sum;
-    const bool row_ok = tid < p.tokens;
-    const long long ob = ((long long)(cell * p.tokens + tid)) * p.D + head * p.hd;
-    for (int c = 0; c < p.hdp / 16; ++c) {
-      float o[16];
-      tmem_ld16(tmem_base + 256 + sl * 64 + lane_addr + c * 16, o);
-      if (row_ok) {
+    wg_sync(wg);
+    // ---- O = P V --------------------------------------------------------------------------------------
+    if (leader) {
+      tcgen05_fence_after();
+      mbar_wait(bar_v, ph);
+      const uint32_t pa[3] = {64, 0, 0};                      // P_lo, P_hi, P_hi
+      const int pb[3] = {0, 1, 0};                            // V_hi, V_lo, V_hi
+      uint32_t acc = 0;
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t vb = smem_u32(v_s[pb[ps]]);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int d = c * 16 + q4 * 4;
-          if (d < p.hd) {
-            bf16 h[4], l[4];
+        for (int kk = 0; kk < TP / 16; ++kk) {
+          umma_bf16_ts(tmem_o, tmem_sp + pa[ps] + kk * 8, make_smem_desc_mn(vb + kk * 2048), idesc_o, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tcgen05_fence_after();
+    if (leader && k + 1 < my_items) load_v(item + stride);      // V tiles are dead
+    // ---- normalise, split, store ------------------------------------------------------------------------
+    {
+      const float inv = 1.0f / sum;
+      const bool row_ok = row < p.tokens;
+      const long long ob = ((long long)(cell * p.tokens + row)) * p.D + head * p.hd;
+      for (int c = 0; c < p.hdp / 16; ++c) {
+        float o[16];
+        tmem_ld16(tmem_o + lane_addr + c * 16, o);
+        if (row_ok) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_bf16(o[q4 * 4 + e] * inv, h[e], l[e]);
-            *reinterpret_cast<uint2*>(out_hi + ob + d) = *reinterpret_cast<const uint2*>(h);
-            *reinterpret_cast<uint2*>(out_lo + ob + d) = *reinterpret_cast<const uint2*>(l);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int d = c * 16 + q4 * 4;
+            if (d < p.hd) {
+              uint32_t h[2], l[2];
+              split_bf16x2(o[q4 * 4] * inv, o[q4 * 4 + 1] * inv, h[0], l[0]);
+              split_bf16x2(o[q4 * 4 + 2] * inv, o[q4 * 4 + 3] * inv, h[1], l[1]);
+              *reinterpret_cast<uint2*>(out_hi + ob + d) = make_uint2(h[0], h[1]);
+              *reinterpret_cast<uint2*>(out_lo + ob + d) = make_uint2(l[0], l[1]);
+            }
           }
         }
       }
     }
     tcgen05_fence_before();
-  };
-
-  if (tid == 0) {
-    if (my_items > 0) issue_loads(0, item_of(0));
-    if (my_items > 1) issue_loads(1, item_of(1));
-  }
-  uint32_t ph = 0;                                       // every barrier completes once per pair
-  for (int k = 0; k < my_items; k += 2, ph ^= 1u) {
-    const bool two = k + 1 < my_items;
-    if (tid == 0) {
-      mbar_wait(&bar_qk[0], ph);
-      tcgen05_fence_after();
-      issue_s(0);
-      if (two) {
-        mbar_wait(&bar_qk[1], ph);
-        issue_s(1);
-      }
-    }
-    float sum0, sum1 = 1.f;
-    mbar_wait(&bar_s[0], ph);
-    tcgen05_fence_after();
-    sum0 = softmax_to_p(0);
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&bar_v[0], ph);
-      tcgen05_fence_after();
-      issue_pv(0);
-    }
-    if (two) {
-      mbar_wait(&bar_s[1], ph);
-      tcgen05_fence_after();
-      sum1 = softmax_to_p(1);
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(&bar_v[1], ph);
-        tcgen05_fence_after();
-        issue_pv(1);
-      }
-    }
-    mbar_wait(&bar_o[0], ph);
-    tcgen05_fence_after();
-    if (tid == 0 && k + 2 < my_items) issue_loads(0, item_of(k + 2));     // slot 0's tiles are dead now
-    store_o(0, item_of(k), sum0);
-    if (two) {
-      mbar_wait(&bar_o[1], ph);
-      tcgen05_fence_after();
-      if (tid == 0 && k + 3 < my_items) issue_loads(1, item_of(k + 3));
-      store_o(1, item_of(k + 1), sum1);
-    }
-    __syncthreads();                     // every thread has drained S / O of this pair before the next MMAs overwrite them
+    wg_sync(wg);                           // the whole warpgroup has drained S/P and O before the next MMAs overwrite them
   }
 
   tcgen05_fence_before();
@@ -280,7 +285,7 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
   if (cells <= 0) return RIBCA_OK;
   AttnParams p;
   p.cells = cells; p.tokens = tokens; p.heads = heads; p.hd = hd; p.hdp = (hd + 15) / 16 * 16; p.D = heads * hd;
-  p.scale = 1.0f / sqrtf((float)hd);
+  p.scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
   const int width = 3 * heads * p.hdp;
   const long long M = (long long)cells * tokens;
   const int TP = tokens <= 112 ? 112 : 128;
