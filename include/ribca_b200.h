@@ -167,7 +167,7 @@ int ribca_layernorm_split(const float* x, int M, int D, const float* gamma, cons
  * FP32-pipe kernel, used for the short sequences of the imputer (tokens <= 32) */
 int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head_dim,
                     void* out_split, long long out_plane, ribca_stream_t stream);
-/* the same on the tensor cores (tcgen05, split-bf16 passes) for tokens <= 128: qkv_split is
+/* the same on the tensor cores (tcgen05, split-bf16 passes) for tokens <= 112: qkv_split is
  * [2][M][3][heads][hdp] bf16 with hdp = head_dim rounded up to 16 and exact zeros in the padding */
 int ribca_attention_tc(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads,
                        int head_dim, void* out_split, long long out_plane, ribca_stream_t stream);

@@ -24,9 +24,11 @@ namespace ribca {
 typedef __nv_bfloat16 bf16;
 
 constexpr int kAttThreads = 256;
-constexpr int kQBytes = 128 * 128;            // 128 rows x 64 bf16
-constexpr int kSlotBytes = 6 * 128 * 128;     // Q, K, V x {hi, lo}, sized for TP = 128 (96 KB)
-constexpr int kAttSmemBytes = 2 * kSlotBytes + 1024 + 128;
+// per warpgroup: Q, K, V x {hi, lo} tiles of TP rows x 128 B, + the O staging tile of the TMA store.
+// (the M = 128 MMA reads 128 Q rows: rows TP..127 fall into the K tile that follows - finite garbage
+// that only reaches S rows which are never used)
+__host__ __device__ constexpr int att_slot_bytes(int tp) { return 8 * tp * 128; }
+__host__ __device__ constexpr int att_smem_bytes(int tp) { return 2 * att_slot_bytes(tp) + 1024 + 128; }
 
 struct AttnParams {
   int cells, tokens, heads, hd, hdp, D;
@@ -75,8 +77,11 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 template <int TP>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    const AttnParams p, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                    const __grid_constant__ CUtensorMap tmap_out, const AttnParams p, bf16* __restrict__ out_hi,
+                    bf16* __restrict__ out_lo) {
   constexpr int kKVBytes = TP * 128;
+  constexpr int kQBytes = TP * 128;
+  constexpr int kSlotBytes = att_slot_bytes(TP);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSlotBytes);
@@ -93,6 +98,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (tid == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_kv);
+    prefetch_tmap(&tmap_out);
     for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
@@ -109,6 +115,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* q_s[2] = {slot, slot + kQBytes};
   uint8_t* k_s[2] = {slot + 2 * kQBytes, slot + 2 * kQBytes + kKVBytes};
   uint8_t* v_s[2] = {slot + 4 * kQBytes, slot + 4 * kQBytes + kKVBytes};
+  uint8_t* o_s = slot + 6 * kQBytes;         // [2 planes][tokens rows][hd] bf16, dense, for the TMA store
+  const bool tma_out = (p.hd % 8) == 0;      // rows of hd * 2 bytes must be multiples of 16 B for the bulk store
 
   const uint32_t idesc_s = make_instr_desc(128, TP, false);
   const uint32_t idesc_o = make_instr_desc(128, p.hdp, true);
@@ -158,7 +166,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // ---- softmax of this thread's row; P -> TMEM over S -----------------------------------------------
     float s[TP];
 #pragma unroll
-    for (int c = 0; c < TP / 16; ++c) tmem_ld16(tmem_sp + lane_addr + c * 16, s + c * 16);
+    for (int c = 0; c < TP / 16; ++c) tmem_ld16_nowait(tmem_sp + lane_addr + c * 16, reinterpret_cast<uint32_t*>(s) + c * 16);
+    tmem_ld_wait();
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < TP; ++j) {
@@ -214,28 +223,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     {
       const float inv = 1.0f / sum;
       const bool row_ok = row < p.tokens;
-      const long long ob = ((long long)(cell * p.tokens + row)) * p.D + head * p.hd;
-      for (int c = 0; c < p.hdp / 16; ++c) {
-        float o[16];
-        tmem_ld16(tmem_o + lane_addr + c * 16, o);
+      float o[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c * 16 < p.hdp) tmem_ld16_nowait(tmem_o + lane_addr + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
+      tmem_ld_wait();
+      if (tma_out) {
+        // the previous item's bulk store must have finished reading the staging tile
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        wg_sync(wg);
+        if (row_ok) {
+          const int row_b = p.hd * 2;
+          uint8_t* dh = o_s + row * row_b;
+          uint8_t* dl = o_s + p.tokens * row_b + row * row_b;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            if (ch * 8 < p.hd) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_bf16x2(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, h[e], l[e]);
+              *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        wg_sync(wg);
+        if (leader) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * p.hd), "r"(cell * p.tokens), "r"(0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        const long long ob = ((long long)(cell * p.tokens + row)) * p.D + head * p.hd;
         if (row_ok) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int d = c * 16 + q4 * 4;
+          for (int q4 = 0; q4 < 16; ++q4) {
+            const int d = q4 * 4;
             if (d < p.hd) {
               uint32_t h[2], l[2];
-              split_bf16x2(o[q4 * 4] * inv, o[q4 * 4 + 1] * inv, h[0], l[0]);
-              split_bf16x2(o[q4 * 4 + 2] * inv, o[q4 * 4 + 3] * inv, h[1], l[1]);
+              split_bf16x2(o[d] * inv, o[d + 1] * inv, h[0], l[0]);
+              split_bf16x2(o[d + 2] * inv, o[d + 3] * inv, h[1], l[1]);
               *reinterpret_cast<uint2*>(out_hi + ob + d) = make_uint2(h[0], h[1]);
               *reinterpret_cast<uint2*>(out_lo + ob + d) = make_uint2(l[0], l[1]);
             }
           }
         }
+        tcgen05_fence_before();
+        wg_sync(wg);
       }
     }
-    tcgen05_fence_before();
-    wg_sync(wg);                           // the whole warpgroup has drained S/P and O before the next MMAs overwrite them
+    // (the barrier inside the output phase orders this warpgroup's TMEM reads before the next item's MMAs)
   }
+  if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
   tcgen05_fence_before();
   __syncthreads();
@@ -261,7 +303,9 @@ static int make_qkv_map(CUtensorMap* map, const void* base, long long plane_elem
 }
 
 template <int TP>
-static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnParams& p, bf16* hi, bf16* lo, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const AttnParams& p, bf16* hi, bf16* lo,
+                     cudaStream_t st) {
+  constexpr int kAttSmemBytes = att_smem_bytes(TP);
   static bool attr_set = false;
   if (!attr_set) {
     RIBCA_TRY(check_cuda(cudaFuncSetAttribute(attention_tc_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes),
@@ -271,7 +315,7 @@ static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnPa
   const int grid = std::min(p.cells * p.heads, num_sms());
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)p.cells * p.heads * (double)p.tokens * p.tokens * p.hd, st);
-  attention_tc_kernel<TP><<<grid, kAttThreads, kAttSmemBytes, st>>>(mq, mkv, p, hi, lo);
+  attention_tc_kernel<TP><<<grid, kAttThreads, kAttSmemBytes, st>>>(mq, mkv, mo, p, hi, lo);
   if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("attention_tc_kernel");
   return RIBCA_OK;
@@ -280,7 +324,7 @@ static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const AttnPa
 // qkv_split: [2][M][3*heads*hdp] bf16, plane stride qkv_plane elements; out_split [2][M][heads*hd]
 int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads, int hd,
                         void* out_split, long long out_plane, cudaStream_t st) {
-  RIBCA_REQUIRE(tokens > 0 && tokens <= 128, "attention_tc: tokens=%d outside [1,128]", tokens);
+  RIBCA_REQUIRE(tokens > 0 && tokens <= 112, "attention_tc: tokens=%d outside [1,112]", tokens);
   RIBCA_REQUIRE(hd > 0 && hd <= 64 && hd % 4 == 0, "attention_tc: head_dim=%d unsupported", hd);
   if (cells <= 0) return RIBCA_OK;
   AttnParams p;
@@ -288,13 +332,25 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
   const int width = 3 * heads * p.hdp;
   const long long M = (long long)cells * tokens;
-  const int TP = tokens <= 112 ? 112 : 128;
+  constexpr int TP = 112;
   CUtensorMap mq, mkv;
-  RIBCA_TRY(make_qkv_map(&mq, qkv_split, qkv_plane, M, width, 128));
+  RIBCA_TRY(make_qkv_map(&mq, qkv_split, qkv_plane, M, width, TP));
   RIBCA_TRY(make_qkv_map(&mkv, qkv_split, qkv_plane, M, width, TP));
+  CUtensorMap mo;
+  memset(&mo, 0, sizeof(mo));
+  if (hd % 8 == 0) {      // output map: [2][M][D] bf16, one box = (head_dim cols, tokens rows, 2 planes), dense rows
+    auto encode = tensor_map_encode_fn();
+    cuuint64_t dims[3] = {(cuuint64_t)p.D, (cuuint64_t)M, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)p.D * 2, (cuuint64_t)out_plane * 2};
+    cuuint32_t box[3] = {(cuuint32_t)hd, (cuuint32_t)tokens, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out_split, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("attention: cuTensorMapEncodeTiled(out) failed (%d)", (int)r); return RIBCA_ECUDA; }
+  }
   bf16* hi = static_cast<bf16*>(out_split);
   bf16* lo = hi + out_plane;
-  return TP == 112 ? launch_tc<112>(mq, mkv, p, hi, lo, st) : launch_tc<128>(mq, mkv, p, hi, lo, st);
+  return launch_tc<TP>(mq, mkv, mo, p, hi, lo, st);
 }
 
 }  // namespace ribca

@@ -355,7 +355,7 @@ static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int head
   const long long pa = (long long)M * D, ph = (long long)M * 4 * D;
   const int hd = D / heads, hdp = (hd + 15) / 16 * 16;
   const int Wq = 3 * heads * hdp;                       // head-padded qkv width
-  const bool tensor_attention = tokens > 32;            // tcgen05 for the classifiers, FP32 pipe for the imputer
+  const bool tensor_attention = tokens > 32 && tokens <= 112;   // tcgen05 for the classifiers, FP32 pipe for the imputer
   RIBCA_REQUIRE(tensor_attention || hdp == hd, "short-sequence attention needs head_dim %% 16 == 0");
   for (int l = 0; l < depth; ++l) {
     const ribca_block_desc& w = blocks[l];
