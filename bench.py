@@ -240,7 +240,7 @@ def main():
     import ctypes as C
     L.ribca_profile_begin()
     hp.run(img_dev, mask_d, to_host=False)
-    nc = 3
+    nc = 7
     ms = (C.c_double * nc)(); ln = (C.c_longlong * nc)(); wk = (C.c_double * nc)()
     _lib.check(L.ribca_profile_end(ms, ln, wk, nc), "ribca_profile_end")
     pk, pk_src = peaks()
@@ -256,6 +256,23 @@ def main():
                     "attention_kernel": {"ms_per_step": ms[1], "launches": int(ln[1]), "tflops_fp32": wk[1] / (ms[1] / 1000) / 1e12 if ms[1] > 0 else 0},
                     "build_patches_kernel": {"ms_per_step": ms[2], "launches": int(ln[2]), "achieved_gbs": wk[2] / (ms[2] / 1000) / 1e9 if ms[2] > 0 else 0,
                                              "frac_of_hbm": (wk[2] / (ms[2] / 1000) / 1e9 / pk["hbm_gbs"]) if ms[2] > 0 else 0}}}
+
+    hbm = pk["hbm_gbs"]
+
+    def hbm_stage(i):
+        gbs = wk[i] / (ms[i] / 1000) / 1e9 if ms[i] > 0 else 0.0
+        return {"ms_per_step": ms[i], "launches": int(ln[i]), "algorithmic_bytes": wk[i], "achieved_gbs": gbs, "frac_of_hbm": gbs / hbm}
+
+    stages = {   # every stage against its roofline (SURVEY 8d work definitions), same profiled step
+        "1_normalize": dict(hbm_stage(3), note="FP64-pipe bound: 161-tap separable FIR in scipy's exact order (~650 flop per 8 algorithmic bytes)"),
+        "2_cell_stats": hbm_stage(4),
+        "3_build_patches": hbm_stage(2),
+        "4_gemm_tcgen05": {"ms_per_step": ms[0], "launches": int(ln[0]), "algorithmic_tflops": gemm_tf, "frac_of_tensor_sustained": gemm_tf / peak_tf,
+                           "issued_frac": passes * gemm_tf / peak_tf},
+        "4_attention_tc": {"ms_per_step": ms[1], "launches": int(ln[1]), "algorithmic_tflops": wk[1] / (ms[1] / 1000) / 1e12 if ms[1] > 0 else 0.0},
+        "4_layernorm": hbm_stage(5),
+        "5_merge": hbm_stage(6),
+    }
 
     # ---- CPU baseline + label agreement on a bounded sample (rank 0, N = 1 only) -------------------------
     cpu_baseline, agreement = None, None
@@ -290,7 +307,7 @@ def main():
                     "h2d_bytes_per_step": int(img_host.numel() * 2 + mask_host.numel() * 4),
                     "d2h_bytes_per_step": int(n_cells * 5 + 18 * 8)},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_sample": agreement,
+            "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline, "parity_sample": agreement,
             "label_histogram": {ALL_TYPES[k]: int(v) for k, v in enumerate(hist) if v},
         }
         print(json.dumps(out))

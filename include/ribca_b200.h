@@ -62,7 +62,11 @@ long long ribca_launch_count(void);
 #define RIBCA_PROF_GEMM 0
 #define RIBCA_PROF_ATTENTION 1
 #define RIBCA_PROF_PATCHES 2
-#define RIBCA_PROF_CLASSES 3
+#define RIBCA_PROF_NORMALIZE 3   /* whole ribca_normalize call; work = C*H*W*(2*sizeof(in)+4) bytes */
+#define RIBCA_PROF_CELLSTATS 4   /* ribca_cell_stats;           work = H*W*4 bytes                    */
+#define RIBCA_PROF_LAYERNORM 5   /* work = M*D*8 bytes                                                */
+#define RIBCA_PROF_MERGE 6       /* work = n*(4*classes+5) bytes                                      */
+#define RIBCA_PROF_CLASSES 7
 int ribca_profile_begin(void);
 int ribca_profile_end(double* ms, long long* launches, double* work, int n_classes);
 

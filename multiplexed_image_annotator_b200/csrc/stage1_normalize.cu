@@ -385,19 +385,31 @@ int ribca_normalize(const void* img, int dtype, int C, int H, int W, const doubl
   float* tmp = static_cast<float*>(workspace);
   SelectState* st = reinterpret_cast<SelectState*>(static_cast<char*>(workspace) + align_up((size_t)hw * sizeof(float), 256));
   cudaStream_t s = as_stream(stream);
+  const bool prof = profiling();
+  if (prof) {
+    const double in_b = dtype == RIBCA_U8 ? 1.0 : (dtype == RIBCA_U16 ? 2.0 : 4.0);
+    prof_begin_span(RIBCA_PROF_NORMALIZE, (double)C * (double)hw * (2.0 * in_b + 4.0), s);
+  }
+  int rc;
   switch (dtype) {
     case RIBCA_U8:
-      return normalize_typed<uint8_t>(static_cast<const uint8_t*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      rc = normalize_typed<uint8_t>(static_cast<const uint8_t*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      break;
     case RIBCA_U16:
-      return normalize_typed<uint16_t>(static_cast<const uint16_t*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      rc = normalize_typed<uint16_t>(static_cast<const uint16_t*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      break;
     case RIBCA_F32:
-      return normalize_typed<float>(static_cast<const float*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      rc = normalize_typed<float>(static_cast<const float*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      break;
     case RIBCA_I32:
-      return normalize_typed<int32_t>(static_cast<const int32_t*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      rc = normalize_typed<int32_t>(static_cast<const int32_t*>(img), C, H, W, bg, has_blur ? &blur : nullptr, k_lo, k_hi, gamma, out, chan_stats, tmp, st, s);
+      break;
     default:
       set_error("ribca_normalize: unsupported dtype %d", dtype);
-      return RIBCA_EUNSUPPORTED;
+      rc = RIBCA_EUNSUPPORTED;
   }
+  if (prof) prof_end_span(s);
+  return rc;
 }
 
 }  // extern "C"

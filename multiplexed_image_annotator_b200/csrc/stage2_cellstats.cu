@@ -182,6 +182,8 @@ int ribca_cell_stats(const int32_t* mask, int H, int W, int max_id, int32_t* bbo
   RIBCA_REQUIRE(H > 0 && W > 0 && max_id >= 0, "ribca_cell_stats: bad shape H=%d W=%d max_id=%d", H, W, max_id);
   cudaStream_t st = as_stream(stream);
   int n_ids = max_id + 1;
+  const bool prof = profiling();
+  if (prof) prof_begin_span(RIBCA_PROF_CELLSTATS, (double)H * (double)W * 4.0, st);
   stats_init_kernel<<<(n_ids + 255) / 256, 256, 0, st>>>(bbox, sums, count, n_ids);
   RIBCA_LAUNCH_CHECK("stats_init_kernel");
   long long total = (long long)H * ((W + kPixPerThread - 1) / kPixPerThread);
@@ -191,6 +193,7 @@ int ribca_cell_stats(const int32_t* mask, int H, int W, int max_id, int32_t* bbo
     cell_stats_kernel<true><<<blocks, 256, 0, st>>>(mask, H, W, max_id, bbox, sums, count);
   else
     cell_stats_kernel<false><<<blocks, 256, 0, st>>>(mask, H, W, max_id, bbox, sums, count);
+  if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("cell_stats_kernel");
   return RIBCA_OK;
 }

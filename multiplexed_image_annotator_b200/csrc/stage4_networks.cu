@@ -301,7 +301,10 @@ int layernorm_launch(const float* x, int M, int D, const float* g, const float* 
   RIBCA_REQUIRE(D % 4 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 4 and <= 1024", D);
   if (M <= 0) return RIBCA_OK;
   bf16* hi = static_cast<bf16*>(out_split);
+  const bool prof = profiling();
+  if (prof) prof_begin_span(RIBCA_PROF_LAYERNORM, (double)M * (double)D * 8.0, st);
   layernorm_split_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, M, D, g, b, eps, hi, hi + out_plane);
+  if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("layernorm_split_kernel");
   return RIBCA_OK;
 }

@@ -120,7 +120,10 @@ extern "C" int ribca_merge_votes(const float* probs0, int classes0, const int* h
   }
   for (int t = 0; t < kTypes; ++t) prm.type_thresh[t] = h_type_thresh[t];
   prm.confidence = confidence;
+  const bool prof = profiling();
+  if (prof) prof_begin_span(RIBCA_PROF_MERGE, (double)n_cells * (4.0 * (prm.classes[0] + prm.classes[1]) + 5.0), as_stream(stream));
   merge_votes_kernel<<<(n_cells + 255) / 256, 256, 0, as_stream(stream)>>>(probs0, probs1, n_cells, prm, label, conf, counts);
+  if (prof) prof_end_span(as_stream(stream));
   RIBCA_LAUNCH_CHECK("merge_votes_kernel");
   return RIBCA_OK;
 }
