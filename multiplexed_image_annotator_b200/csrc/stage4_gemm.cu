@@ -23,6 +23,9 @@
 //                (cp.reduce.async.bulk.tensor .add.f32), so x is never read into the SM.
 //                TMEM is double-buffered (2 x 256 columns): the epilogue of tile t overlaps the main
 //                loop of tile t+1
+//   CTAs run as clusters of two that own vertically adjacent M tiles of the same N block: each loads
+//   half of the W tile and TMA-multicasts it to both (W crosses L2 -> shared memory once per pair);
+//   a ring slot is released when BOTH issuers' tcgen05.commit (multicast) have arrived.
 //   tiles are ordered m-major so the CTAs of one wave share A rows through L2 and W stays L2-resident.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -73,7 +76,8 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
                                               uint64_t* tmem_empty, int warp, int lane) {
   const int BN = shp.BN;
   const int n_tiles_n = shp.N / BN;
-  const int n_tiles = ((shp.M + BM - 1) / BM) * n_tiles_n;
+  const int n_pairs = (((shp.M + BM - 1) / BM + 1) / 2) * n_tiles_n;
+  const int cta_rank = (int)cluster_ctarank();
   const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
   const int half = (warp - 2) >> 2;                      // which of the two warps of the quadrant
   uint8_t* stg = staging_base + (warp - 2) * kStagingBytes;
@@ -81,10 +85,10 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   const bool split_out = epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT;
   const int n_chunks = BN / CW;
   int local = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+  for (int pr = blockIdx.x >> 1; pr < n_pairs; pr += gridDim.x >> 1, ++local) {
     const int buf = local & 1;
     const uint32_t use = (uint32_t)(local >> 1);
-    const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+    const int m0 = (2 * (pr / n_tiles_n) + cta_rank) * BM, n0 = (pr % n_tiles_n) * BN;
     const int row = m0 + quad * 32 + lane;
     const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
     mbar_wait(&tmem_full[buf], use & 1u);
@@ -163,7 +167,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmShape shp, const GemmEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
@@ -181,7 +185,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int BN = shp.BN;
   const int n_tiles_n = shp.N / BN;
   const int n_tiles_m = (shp.M + BM - 1) / BM;
-  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_pairs = ((n_tiles_m + 1) / 2) * n_tiles_n;   // a pair = M tiles (2p, 2p+1) x one N block, one per CTA of the cluster
+  const uint32_t cta_rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int n_kb = (shp.K + BK - 1) / BK;
   const int n_iter = n_kb;
   const int w_tile = BN * BK * 2;                        // one plane of the W tile
@@ -191,13 +197,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_out);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }   // both CTAs' issuers release a slot
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();                 // the peer's barriers are initialised before any multicast can reach them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -205,15 +212,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      const int w_half_rows = BN / 2;
+      for (int pr = pair0; pr < n_pairs; pr += pair_stride) {
+        const int m0 = (2 * (pr / n_tiles_n) + (int)cta_rank) * BM, n0 = (pr % n_tiles_n) * BN;
         for (int kb = 0; kb < n_iter; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);        // released by both CTAs: the peer multicasts into this slot too
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], stage_tx);
+          mbar_expect_tx(&full_bar[stage], stage_tx);      // own A + both halves of W (own multicast + the peer's)
           tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, 0);      // box depth = n_planes: hi tile, then lo tile
-          tma_load_3d(sb, &tmap_w, &full_bar[stage], kb * BK, n0, 0);
+          for (int pl = 0; pl < shp.n_planes; ++pl)
+            tma_load_3d_mcast(sb + pl * w_tile + (int)cta_rank * w_half_rows * BK * 2, &tmap_w, &full_bar[stage], kb * BK,
+                              n0 + (int)cta_rank * w_half_rows, pl, (uint16_t)0x3);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -224,7 +234,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t idesc = make_instr_desc(BM, BN);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+      for (int pr = pair0; pr < n_pairs; pr += pair_stride, ++local) {
         const int buf = local & 1;
         const uint32_t use = (uint32_t)(local >> 1);
         mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);      // epilogue has drained this accumulator
@@ -253,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               umma_bf16(d_tmem, make_smem_desc_sw64(a_addr + k * UMMA_K * 2), make_smem_desc_sw64(b_addr + k * UMMA_K * 2),
                         idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                  // slot reusable once these MMAs retire
+          umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);   // slot reusable (in both CTAs) once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[buf]);                      // accumulator complete
@@ -267,6 +277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();                 // no CTA exits while its peer can still multicast into it
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
@@ -430,7 +441,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1, "gemm: unknown precision %d", precision);
   CUtensorMap map_a, map_w, map_out;
   RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
-  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN, shp.n_planes));
+  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN / 2, 1));      // each CTA of a pair loads (and multicasts) half of the W tile
   epi.chunk = shp.BN % 32 == 0 ? 32 : 16;
   RIBCA_REQUIRE(!split_out || (out_plane * 2) % 16 == 0, "gemm: split output plane stride must be 16-byte aligned");
   RIBCA_TRY(make_output_map(&map_out, split_out, split_out ? out_split : (void*)out_f32, out_plane, M, N, epi.chunk));
@@ -440,8 +451,8 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
                          "cudaFuncSetAttribute(gemm_tcgen05_kernel)"));
     attr_set = true;
   }
-  const int n_tiles = ((M + BM - 1) / BM) * (N / shp.BN);
-  const int grid = std::min(n_tiles, num_sms());
+  const int n_pairs = (((M + BM - 1) / BM + 1) / 2) * (N / shp.BN);
+  const int grid = 2 * std::min(n_pairs, num_sms() / 2);
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream);
   gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, map_out, shp, epi);
