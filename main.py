@@ -32,28 +32,28 @@ def batch_run(marker_list_path, image_path, device, main_dir, batch_id, bs, stri
     _pipeline(annotator, bs, n_regions, export_before_regions=True, from_script=True)
 
 
+# flag, type (None = store_true), default, required  -- names and defaults of reference main.py:60-104
+_OPTIONS = (
+    ("--marker-list-path", str, None, True), ("--device", str, "cuda", False), ("--main-dir", str, "./", False),
+    ("--batch-id", str, None, True), ("--strict", None, False, False), ("--infer", None, True, False),
+    ("--min-cells", int, -1, False), ("--n-regions", int, 3, False), ("--normalize", None, True, False),
+    ("--blur", float, 0.3, False), ("--amax", float, 99.8, False), ("--confidence", float, 0.3, False),
+    ("--cell-type-confidence", float, None, False), ("--bs", int, 128, False), ("--cell-size", int, 30, False),
+    ("--n_jobs", int, 0, False),
+)
+
+
 def parse_args(argv=None):
-    ap = argparse.ArgumentParser(description='Process images with markers')
-    ap.add_argument('--marker-list-path', type=str, required=True, help='Path to the markers text file')
-    ap.add_argument('--device', type=str, default='cuda', help='Device to run on (cuda)')
-    ap.add_argument('--main-dir', type=str, default='./', help='Main directory path')
-    ap.add_argument('--batch-id', type=str, required=True, help='Batch identifier')
-    ap.add_argument('--strict', action='store_true', help='Enable strict mode')
-    ap.add_argument('--infer', action='store_true', default=True, help='Enable inference')
-    ap.add_argument('--min-cells', type=int, default=-1, help='Minimum number of cells')
-    ap.add_argument('--n-regions', type=int, default=3, help='Number of regions')
-    ap.add_argument('--normalize', action='store_true', default=True, help='Enable normalization')
-    ap.add_argument('--blur', type=float, default=0.3, help='Blur factor')
-    ap.add_argument('--amax', type=float, default=99.8, help='Maximum amplitude')
-    ap.add_argument('--confidence', type=float, default=0.3, help='Confidence threshold')
-    ap.add_argument('--cell-type-confidence', type=float, default=None, help='Cell type confidence threshold')
-    ap.add_argument('--bs', type=int, default=128, help='Batch size')
-    ap.add_argument('--cell-size', type=int, default=30, help='Cell size')
-    ap.add_argument('--n_jobs', type=int, default=0, help='Cell size')
-    group = ap.add_mutually_exclusive_group(required=True)
-    group.add_argument('--image-path', type=str, help='Path to single image file')
-    group.add_argument('--batch-csv', type=str, help='Path to CSV file for batch processing')
-    ap.add_argument('--mask-path', type=str, help='Path to mask file (required for single image mode)')
+    ap = argparse.ArgumentParser(description="RIBCA cell-type annotation on B200 (reference-compatible flags)")
+    for flag, kind, default, required in _OPTIONS:
+        if kind is None:                                   # `store_true` with default True cannot be switched off,
+            ap.add_argument(flag, action="store_true", default=default)       # exactly as in the reference CLI
+        else:
+            ap.add_argument(flag, type=kind, default=default, required=required)
+    src = ap.add_mutually_exclusive_group(required=True)
+    src.add_argument("--image-path", type=str, help="single image (needs --mask-path)")
+    src.add_argument("--batch-csv", type=str, help="CSV with columns image_path,mask_path")
+    ap.add_argument("--mask-path", type=str)
     args = ap.parse_args(argv)
     if args.image_path and not args.mask_path:
         ap.error("--mask-path is required when using --image-path")

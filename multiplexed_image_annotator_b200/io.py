@@ -6,6 +6,9 @@ they can be pinned and copied to the device in one transfer.
 """
 from __future__ import annotations
 
+import os
+import time
+
 import numpy as np
 
 
@@ -53,3 +56,35 @@ def read_mask(path: str) -> np.ndarray:
     if m.ndim == 3:
         m = m[:, :, 0]
     return np.ascontiguousarray(m.astype(np.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# run log: file name and line format of the reference (`<main_dir>/results/log.txt`, a creation line, then
+# one message per line; reference cta/logger.py).  Line-buffered: the reference's callers never close it.
+# ------------------------------------------------------------------------------------------------
+class RunLog:
+    FILE = "results/log.txt"
+
+    def __init__(self, main_dir):
+        os.makedirs(os.path.join(main_dir, "results"), exist_ok=True)
+        self.log_file_path = os.path.join(main_dir, self.FILE)
+        self.log_file = open(self.log_file_path, "w", buffering=1)
+        self.log(f"Log file created at {time.ctime()}")
+
+    def log(self, message):
+        if not self.log_file.closed:
+            print(str(message), file=self.log_file)
+
+    def log_all_hyperparameters(self, hyperparameters):
+        self.log("Hyperparameters:")
+        for name, value in hyperparameters.items():
+            self.log(f"{name}: {value}")
+
+    def close(self):
+        self.log_file.close()
+
+    def __del__(self):
+        try:
+            self.log_file.close()
+        except Exception:
+            pass

@@ -9,5 +9,6 @@ run stages python -m pytest tests/test_gpu_stages.py -q -m gpu --timeout 300 -p 
 run gemm python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "gemm or layernorm or attention"
 run networks python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "vit or mae"
 run e2e python -m pytest tests/test_gpu_networks.py -q -m gpu --timeout 300 -p no:cacheprovider -s -k "annotator"
+run fullsize python -m pytest tests/test_gpu_fullsize.py -q -m gpu --timeout 400 -p no:cacheprovider
 run smoke python __graft_entry__.py smoke
 cat gpurun_out/summary.txt
