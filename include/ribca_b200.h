@@ -142,6 +142,18 @@ int ribca_build_patches(const float* img, const int32_t* mask, int C_img, int H,
                         const double* h_gauss, double* avg_int, int32_t* windows,
                         ribca_stream_t stream);
 
+/* The same for cell_size != 30 (cta/preprocess.py:67,78,106): the window edge is patch_edge =
+ * int(40 * cell_size / 30) (<= 80), and the float64 patch is resampled to 40 x 40 like
+ * skimage.transform.resize(order=0, anti_aliasing=True, preserve_range=True): Gaussian of sigma
+ * (patch_edge/40 - 1)/2 ('mirror', half kernel h_w_aa[0..r_aa], r_aa <= 0 = none), nearest source indices
+ * h_src_index[40] (scipy zoom grid_mode arithmetic, computed by the host), clip to the patch range. */
+int ribca_build_patches_resized(const float* img, const int32_t* mask, int C_img, int H, int W,
+                                const float* min_val, const int32_t* ids, const int32_t* cbbox,
+                                int cell_begin, int n_cells, int n_panels, const int* h_n_ch,
+                                const int* h_chan_index, float* const* h_out, const double* h_gauss,
+                                int patch_edge, const int* h_src_index, const double* h_w_aa, int r_aa,
+                                double* avg_int, int32_t* windows, ribca_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 4 - networks.  replaces VisionTransformer / vit_* and _predict_cell_types' forward +
  * softmax (cta/model.py:31-88, 397-406) and MaskedAutoencoderViT / MarkerImputer.impute

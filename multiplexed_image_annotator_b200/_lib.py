@@ -115,6 +115,8 @@ SIGNATURES = {
     "ribca_compact_cells": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "ribca_build_patches": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I),
                                  C.POINTER(_P), C.POINTER(_D), _P, _P, _P]),
+    "ribca_build_patches_resized": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I),
+                                         C.POINTER(_P), C.POINTER(_D), _I, C.POINTER(_I), C.POINTER(_D), _I, _P, _P, _P]),
     "ribca_gemm_splitbf16": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _P, _I, _I, _P, _P, _LL, _I, _P]),
     "ribca_split_bf16": (_I, [_P, _LL, _P, _P, _P]),
     "ribca_layernorm_split": (_I, [_P, _I, _I, _P, _P, _F, _P, _LL, _P]),

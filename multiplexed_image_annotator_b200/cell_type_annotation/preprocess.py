@@ -95,9 +95,10 @@ class ImageProcessor(object):
         if str(device).startswith("cpu"):
             raise RuntimeError("the B200 build has no CPU path: pass device='cuda' (the reference's CPU path is the oracle)")
         self.device = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
-        if int(cell_size) != 30:
-            raise NotImplementedError("cell_size != 30 (patch resampling) is not built yet; see DESIGN.md 'next'")
+        self.cell_size = cell_size
         self.scale = cell_size / 30.0
+        if not 8 <= int(40 * self.scale) <= 80:
+            raise ValueError("cell_size must give a patch edge int(40 * cell_size / 30) in [8, 80] (cell_size 6..60)")
         self.n_jobs = n_jobs
         # device-side state per image
         self.images_dev, self.masks_dev, self.cells, self.min_val = [], [], [], []
@@ -165,7 +166,7 @@ class ImageProcessor(object):
         for a in range(lo, hi, chunk):
             b = min(a + chunk, hi)
             outs, avg, _ = ops.build_patches(self.images_dev[i], self.masks_dev[i], self.min_val[i], self.cells[i], idx,
-                                             a, b - a, want_intensity=want_intensity)
+                                             a, b - a, want_intensity=want_intensity, cell_size=self.cell_size)
             batch = dict(zip(panels, outs))
             for p in panels:
                 imp = self._imputer_for(p)

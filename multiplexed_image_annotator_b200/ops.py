@@ -181,9 +181,30 @@ def _gauss_table() -> np.ndarray:
     return _GAUSS
 
 
+def resize_plan(patch_edge: int):
+    """Host plan of skimage.transform.resize((C, P, P) -> (C, 40, 40), order=0, anti_aliasing=True):
+    (source index per output row/column, anti-alias half kernel, radius).  The index arithmetic is
+    scipy.ndimage.zoom's (grid_mode=True, order 0): cc = (k + 0.5) * zoom - 0.5, idx = floor(cc + 0.5),
+    with zoom = P / 40 in float64."""
+    zoom = np.divide(np.array([patch_edge]), np.array([PATCH]), out=np.ones(1, dtype=np.float64))[0]
+    idx = []
+    for k in range(PATCH):
+        cc = float(k)
+        cc += 0.5
+        cc *= zoom
+        cc -= 0.5
+        idx.append(int(np.floor(cc + 0.5)))
+    sigma = max(0.0, (patch_edge / PATCH - 1) / 2)
+    if sigma > 0:
+        w, r = gaussian_half_kernel(sigma)
+    else:
+        w, r = np.zeros(1), -1
+    return np.asarray(idx, dtype=np.int32), np.ascontiguousarray(w, dtype=np.float64), r
+
+
 def build_patches(img: torch.Tensor, mask: torch.Tensor, min_val: torch.Tensor, cells: CellTable, panels,
                   cell_begin: int = 0, n_cells: int | None = None, want_intensity: bool = False,
-                  want_windows: bool = False):
+                  want_windows: bool = False, cell_size=30):
     """crop_cell + smooth + channel select for cells [cell_begin, cell_begin + n_cells).
     panels: list of channel-index lists (may contain -1).  Returns (list of (n, C_p, 40, 40) float32
     tensors, avg_int (n, C_img) float64 or None, windows (n, 4) int32 or None)."""
@@ -210,9 +231,17 @@ def build_patches(img: torch.Tensor, mask: torch.Tensor, min_val: torch.Tensor, 
     avg = torch.empty((n, c_img), dtype=torch.float64, device=dev) if want_intensity else None
     wins = torch.empty((n, 4), dtype=torch.int32, device=dev) if want_windows else None
     g = _gauss_table()
-    _lib.check(L.ribca_build_patches(_ptr(img), _ptr(mask), c_img, h, w, _ptr(min_val), _ptr(cells.ids), _ptr(cells.bbox),
-                                     cell_begin, n, npan, n_ch, idx, out_ptrs, _dptr(g), _ptr(avg), _ptr(wins), _stream()),
-               "ribca_build_patches")
+    edge = int(PATCH * (cell_size / 30.0))                    # reference preprocess.py:67,78
+    if edge == PATCH:
+        _lib.check(L.ribca_build_patches(_ptr(img), _ptr(mask), c_img, h, w, _ptr(min_val), _ptr(cells.ids), _ptr(cells.bbox),
+                                         cell_begin, n, npan, n_ch, idx, out_ptrs, _dptr(g), _ptr(avg), _ptr(wins), _stream()),
+                   "ribca_build_patches")
+    else:
+        src, w_aa, r_aa = resize_plan(edge)
+        _lib.check(L.ribca_build_patches_resized(_ptr(img), _ptr(mask), c_img, h, w, _ptr(min_val), _ptr(cells.ids),
+                                                 _ptr(cells.bbox), cell_begin, n, npan, n_ch, idx, out_ptrs, _dptr(g), edge,
+                                                 src.ctypes.data_as(C.POINTER(C.c_int)), _dptr(w_aa), r_aa, _ptr(avg), _ptr(wins),
+                                                 _stream()), "ribca_build_patches_resized")
     return outs, avg, wins
 
 

@@ -36,13 +36,14 @@ class HotPath:
 
     def __init__(self, panels: dict, models: dict, imputers: dict | None = None, *, normalization=True, blur=0.3,
                  amax=99.8, confidence=0.3, cell_type_confidence=None, chunk_cells=4096, device="cuda",
-                 shard_cells=True):
+                 shard_cells=True, cell_size=30):
         self.panels, self.models, self.imputers = dict(panels), models, imputers or {}
         self.normalization, self.blur, self.amax = normalization, blur, amax
         self.confidence, self.ctc = confidence, cell_type_confidence
         self.chunk = chunk_cells
         self.device = torch.device(device)
         self.shard_cells = shard_cells
+        self.cell_size = cell_size
         for p in self.panels:
             if not isinstance(models.get(p), VitEngine):
                 raise ValueError(f"no classifier engine for panel {p}")
@@ -71,7 +72,7 @@ class HotPath:
         parts = {p: [] for p in names}
         for a in range(lo, hi, self.chunk):
             b = min(a + self.chunk, hi)
-            outs, _, _ = ops.build_patches(img, msk, mn, cells, idx, a, b - a)
+            outs, _, _ = ops.build_patches(img, msk, mn, cells, idx, a, b - a, cell_size=self.cell_size)
             for p, t in zip(names, outs):
                 if p in self.imputers:
                     eng, present = self.imputers[p]

@@ -15,6 +15,7 @@ inputs; inputs and outputs are stored as compressed .npz / .json so that the tes
   markers.json         MarkerParser.parse on examples/markers.txt and on synthetic marker lists
   normalize.npz        ImageProcessor._normalize on small uint16 stacks (several blur / amax)
   patches.npz          ImageProcessor._img2patches (crop_cell + smooth + resize + channel select)
+  cellsize.npz         the same for cell_size 15 / 20 / 40 / 45 / 60 (patch resampling)
   vit.npz              reference vit_s / vit_tiny forward + softmax on a few patches (seeded weights)
   mae.npz              MarkerImputer.impute on a few cells (seeded weights)
   merge.json           Annotator.merge_by_voting for every reachable branch
@@ -176,6 +177,24 @@ def golden_patches():
         out[tag + "_smooth"] = np.array(sm)
     np.savez_compressed(os.path.join(OUT, "patches.npz"), **out)
     print("patches:", {k: v.shape for k, v in out.items() if k.endswith("_patches")})
+
+
+def golden_cellsize():
+    """_img2patches for cell_size != 30 (patch edge int(40 * cell_size / 30), anti-aliased nearest resize)."""
+    img, mask = _small_scene(150, 170, 5, 41)
+    norm = _processor()._normalize(img.copy(), blur=0.3, amax=99.8)
+    out = {"img_norm": norm, "mask": mask}
+    for cs in (15, 20, 40, 45, 60):
+        proc = _processor(cell_size=cs)
+        d = proc._cell_pos_dict(mask, 0)
+        with tempfile.TemporaryDirectory() as tmp:
+            inten = proc._img2patches(norm, mask, [4, -1, 2, 0], d, None, id="g", save_path=tmp, save_tensor=True,
+                                      int_full=True, batch_size=10000)
+            pt = torch.load(os.path.join(tmp, "g_batch_0.pt")).numpy()
+        out[f"cs{cs}_patches"] = pt[:24]
+        out[f"cs{cs}_intensity"] = inten
+    np.savez_compressed(os.path.join(OUT, "cellsize.npz"), **out)
+    print("cellsize:", {k: v.shape for k, v in out.items() if k.endswith("_patches")})
 
 
 def _ref_vit(panel, sd):
@@ -368,6 +387,6 @@ def golden_e2e():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cells", "markers", "normalize", "patches", "vit", "mae", "merge", "e2e"]
+    which = sys.argv[1:] or ["cells", "markers", "normalize", "patches", "cellsize", "vit", "mae", "merge", "e2e"]
     for name in which:
         globals()["golden_" + name]()

@@ -173,6 +173,21 @@ def test_patches_multi_panel_and_chunks():
         assert torch.equal(part[p], full[p][17:57])
 
 
+@pytest.mark.parametrize("cell_size", [15, 20, 40, 45, 60])
+def test_patches_other_cell_sizes_reference_golden(golden_dir, cell_size):
+    """cell_size != 30: window edge int(40 * cell_size / 30), anti-aliased nearest resize to 40 x 40."""
+    g = _npz(golden_dir, "cellsize.npz")
+    img = torch.from_numpy(g["img_norm"]).to(DEV)
+    m = torch.from_numpy(g["mask"]).to(DEV)
+    tab = ops.cell_stats(m)
+    mn = ops.channel_min(img)
+    (pt,), avg, _ = ops.build_patches(img, m, mn, tab, [[4, -1, 2, 0]], want_intensity=True, cell_size=cell_size)
+    want = g[f"cs{cell_size}_patches"]
+    got = pt.cpu().numpy()[: len(want)]
+    assert np.array_equal(got, want), _report_mismatch(f"cell_size {cell_size}", got, want)
+    np.testing.assert_allclose((avg.cpu().numpy() + 1) / 2, g[f"cs{cell_size}_intensity"], rtol=1e-12, atol=1e-14)
+
+
 # ------------------------------------------------------------------------------------------------
 # stage 5
 # ------------------------------------------------------------------------------------------------

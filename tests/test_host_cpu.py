@@ -78,6 +78,15 @@ def test_gaussian_taps_match_scipy():
         assert r == int(4.0 * float(s) + 0.5) and np.array_equal(full[r:], w)
 
 
+def test_resize_plan_matches_scipy_zoom():
+    import scipy.ndimage as ndi
+    for edge in range(8, 81):
+        idx, w, r = ops.resize_plan(edge)
+        a = np.arange(edge, dtype=np.float64)
+        assert np.array_equal(ndi.zoom(a, 40 / edge, order=0, mode="mirror", grid_mode=True), a[idx]), edge
+        assert r == (int(4.0 * ((edge / 40 - 1) / 2) + 0.5) if edge > 40 else -1)
+
+
 def test_marker_parser_matches_reference(golden_dir, tmp_path):
     cases = json.load(open(os.path.join(golden_dir, "markers.json")))
     for name, case in cases.items():

@@ -80,6 +80,15 @@ def test_patches_bit_exact(golden_dir, tag, maskkey):
         assert np.array_equal(orc.soft_mask(mp, st["ids"][k]), g[tag + "_smooth"][k])
 
 
+@pytest.mark.parametrize("cell_size", [15, 20, 40, 45, 60])
+def test_patches_other_cell_sizes(golden_dir, cell_size):
+    g = _npz(golden_dir, "cellsize.npz")
+    st = orc.cell_stats(g["mask"])
+    pt, inten, _ = orc.build_patches(g["img_norm"], g["mask"], [4, -1, 2, 0], st, cell_size=cell_size, cells=range(24))
+    assert np.array_equal(pt, g[f"cs{cell_size}_patches"])
+    assert np.array_equal(inten, g[f"cs{cell_size}_intensity"][:24])
+
+
 @pytest.mark.parametrize("panel", ["immune_base", "nerve_cell"])
 def test_vit_forward(golden_dir, panel):
     g = _npz(golden_dir, "vit.npz")
