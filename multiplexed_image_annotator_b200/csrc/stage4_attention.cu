@@ -65,15 +65,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// (a, b) -> packed split bf16x2: hi = bf16x2(a, b), lo = bf16x2(a - hi.a, b - hi.b); element a in the low half
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 template <int TP>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
