@@ -23,9 +23,14 @@
 //                (cp.reduce.async.bulk.tensor .add.f32), so x is never read into the SM.
 //                TMEM is double-buffered (2 x 256 columns): the epilogue of tile t overlaps the main
 //                loop of tile t+1
-//   CTAs run as clusters of two that own vertically adjacent M tiles of the same N block: each loads
-//   half of the W tile and TMA-multicasts it to both (W crosses L2 -> shared memory once per pair);
-//   a ring slot is released when BOTH issuers' tcgen05.commit (multicast) have arrived.
+//   CTAs run as PAIRS (cluster of 2, tcgen05 cta_group::2): a pair owns a 256 x BN output tile, each CTA
+//   stages its own 128 rows of A and HALF of the W tile, and the leader CTA issues M = 256 MMAs that read
+//   both CTAs' shared memory.  Per SM this halves the B traffic (L2 -> smem and smem -> tensor core): the
+//   single-CTA M = 128 form needs 96 B/cycle of operand reads plus 64 B/cycle of TMA writes against a
+//   128 B/cycle shared-memory port, which capped the tensor pipe at ~80 %.  All barriers of the main
+//   loop live in the leader: both CTAs' TMA loads complete_tx there; tcgen05.commit multicasts the
+//   slot-free / accumulator-ready signals to both CTAs; the peer's epilogue releases the accumulator by a
+//   remote mbarrier arrive.
 //   tiles are ordered m-major so the CTAs of one wave share A rows through L2 and W stays L2-resident.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -35,13 +40,13 @@ namespace ribca {
 constexpr int BM = 128;
 constexpr int BK = 32;              // 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kEpiWarps = 8;        // two per TMEM lane quadrant, alternating column chunks
 constexpr int kMaxBN = 256;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr int kATile = BM * BK * 2;             // one plane of A:  8 KB
 constexpr int kABytes = 2 * kATile;             // hi + lo:        16 KB
-constexpr int kBBytesMax = 2 * kMaxBN * BK * 2; // W hi + lo:      32 KB
+constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, hi + lo: 16 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kStagingBytes = 4096;           // per epilogue warp: 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo)
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -173,7 +178,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
     }
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);        // the leader's issuer owns the accumulator hand-off
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores of this warp have landed
   __syncwarp();
@@ -202,18 +207,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int n_kb = (shp.K + BK - 1) / BK;
   const int n_iter = n_kb;
-  const int w_tile = BN * BK * 2;                        // one plane of the W tile
-  const uint32_t stage_tx = (uint32_t)(shp.n_planes * (kATile + w_tile));
+  const int w_tile = (BN / 2) * BK * 2;                  // one plane of this CTA's half of the W tile
+  const uint32_t stage_tx = (uint32_t)(2 * shp.n_planes * (kATile + w_tile));   // both CTAs' loads land on the leader's barrier
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_out);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }   // both CTAs' issuers release a slot
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpiWarps); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * kEpiWarps); }   // both CTAs' epilogues
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                 // the peer's barriers are initialised before any multicast can reach them
@@ -221,29 +227,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const int w_half_rows = BN / 2;
       for (int pr = pair0; pr < n_pairs; pr += pair_stride) {
-        const int m0 = (2 * (pr / n_tiles_n) + (int)cta_rank) * BM, n0 = (pr % n_tiles_n) * BN;
+        const int m0 = (2 * (pr / n_tiles_n) + (int)cta_rank) * BM;
+        const int n0 = (pr % n_tiles_n) * BN + (int)cta_rank * (BN / 2);     // this CTA's half of the W tile
         for (int kb = 0; kb < n_iter; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);        // released by both CTAs: the peer multicasts into this slot too
+          mbar_wait(&empty_bar[stage], phase ^ 1u);        // released for both CTAs by the leader's multicast commit
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], stage_tx);      // own A + both halves of W (own multicast + the peer's)
-          tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * BK, m0, 0);      // box depth = n_planes: hi tile, then lo tile
-          for (int pl = 0; pl < shp.n_planes; ++pl)
-            tma_load_3d_mcast(sb + pl * w_tile + (int)cta_rank * w_half_rows * BK * 2, &tmap_w, &full_bar[stage], kb * BK,
-                              n0 + (int)cta_rank * w_half_rows, pl, (uint16_t)0x3);
+          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_3d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m0, 0);    // box depth = n_planes: hi tile, then lo tile
+          tma_load_3d_2sm(sb, &tmap_w, &full_bar[stage], kb * BK, n0, 0);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(BM, BN);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_instr_desc(2 * BM, BN);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int pr = pair0; pr < n_pairs; pr += pair_stride, ++local) {
@@ -265,20 +269,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const uint64_t a_lo = make_smem_desc_sw64(a_addr + kATile + k * UMMA_K * 2);
               const uint64_t w_hi = make_smem_desc_sw64(b_addr + k * UMMA_K * 2);
               const uint64_t w_lo = make_smem_desc_sw64(b_addr + w_tile + k * UMMA_K * 2);
-              umma_bf16(d_tmem, a_lo, w_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(d_tmem, a_hi, w_lo, idesc, 1u);
-              umma_bf16(d_tmem, a_hi, w_hi, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_lo, w_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, a_hi, w_lo, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi, w_hi, idesc, 1u);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16(d_tmem, make_smem_desc_sw64(a_addr + k * UMMA_K * 2), make_smem_desc_sw64(b_addr + k * UMMA_K * 2),
-                        idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, make_smem_desc_sw64(a_addr + k * UMMA_K * 2), make_smem_desc_sw64(b_addr + k * UMMA_K * 2),
+                            idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);   // slot reusable (in both CTAs) once these MMAs retire
+          umma_commit_2sm_mcast(&empty_bar[stage], (uint16_t)0x3);   // slot reusable in both CTAs once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[buf]);                      // accumulator complete
+        umma_commit_2sm_mcast(&tmem_full[buf], (uint16_t)0x3);   // accumulator complete: both CTAs' epilogues
       }
     }
   } else {
@@ -293,7 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
@@ -453,7 +457,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1, "gemm: unknown precision %d", precision);
   CUtensorMap map_a, map_w, map_out;
   RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
-  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN / 2, 1));      // each CTA of a pair loads (and multicasts) half of the W tile
+  RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN / 2, shp.n_planes));      // each CTA of a pair stages half of the W tile
   epi.chunk = shp.BN % 32 == 0 ? 32 : 16;
   RIBCA_REQUIRE(!split_out || (out_plane * 2) % 16 == 0, "gemm: split output plane stride must be 16-byte aligned");
   RIBCA_TRY(make_output_map(&map_out, split_out, split_out ? out_split : (void*)out_f32, out_plane, M, N, epi.chunk));
