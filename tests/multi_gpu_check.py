@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""2-GPU check (run under torchrun on a multi-GPU box, not collected by pytest):
+the cell-range sharded HotPath (every rank holds the image, owns a contiguous range of cells, one
+all_gather of labels / confidences + all_reduce of counts over NCCL) must reproduce the unsharded
+single-rank result bit-for-bit.
+
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multiplexed_image_annotator_b200 import engine, synth, weights          # noqa: E402
+from multiplexed_image_annotator_b200.pipeline import HotPath                # noqa: E402
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rank, world = dist.get_rank(), dist.get_world_size()
+
+mask = synth.synth_mask(1500, 1300, seed=11, device=dev)
+img = torch.from_numpy(synth.to_uint16(synth.synth_image(mask, 10, seed=11))).to(dev)
+idx = {"immune_extended": list(range(10))}
+sd = weights.random_vit_state("immune_extended", seed=5)
+eng = engine.VitEngine("immune_extended", sd, dev)
+single = HotPath(idx, {"immune_extended": eng}, device=dev, shard_cells=False, chunk_cells=1000)
+ref = single.run(img, mask, to_host=False, keep_probs=True)
+cal = weights.calibrate_head(sd, torch.log(ref.probs["immune_extended"][:256]).mean(0).cpu().numpy(), 20.0)   # any fixed head change
+eng.set_head(cal["head.weight"], cal["head.bias"])
+ref = single.run(img, mask, to_host=False)
+sharded = HotPath(idx, {"immune_extended": eng}, device=dev, shard_cells=True, chunk_cells=1000).run(img, mask, to_host=False)
+assert sharded.n_cells == ref.n_cells
+assert torch.equal(sharded.label, ref.label), "labels differ between sharded and single-rank runs"
+assert torch.equal(sharded.confidence, ref.confidence), "confidences differ"
+assert torch.equal(sharded.counts, ref.counts), "counts differ"
+ok = torch.ones(1, device=dev)
+dist.all_reduce(ok)
+if rank == 0:
+    print(f"multi-gpu check ok: world={world} cells={ref.n_cells} labels={len(torch.unique(ref.label))} "
+          f"counts={ref.counts.tolist()}")
+dist.destroy_process_group()

@@ -209,3 +209,31 @@ def test_merge_reference_golden(golden_dir):
         assert np.array_equal(counts.cpu().numpy(), want_counts)
         checked += 1
     assert checked >= 30
+
+
+# ------------------------------------------------------------------------------------------------
+# degenerate inputs through the in-memory pipeline
+# ------------------------------------------------------------------------------------------------
+def test_hot_path_degenerate_inputs():
+    from multiplexed_image_annotator_b200 import engine, weights
+    from multiplexed_image_annotator_b200.pipeline import HotPath
+    eng = engine.VitEngine("nerve_cell", weights.random_vit_state("nerve_cell", seed=1), DEV)
+    hp = HotPath({"nerve_cell": [0, 1, 2]}, {"nerve_cell": eng}, device=DEV, shard_cells=False)
+    rng = np.random.default_rng(3)
+    # no cells at all
+    img = rng.integers(0, 3000, (3, 64, 80)).astype(np.uint16)
+    res = hp.run(img, np.zeros((64, 80), np.int32))
+    assert res.n_cells == 0 and res.label.numel() == 0 and int(res.counts.sum()) == 0
+    # one single-pixel cell in an image smaller than the 40 x 40 patch; an all-zero channel (-> -1 everywhere)
+    img = rng.integers(0, 3000, (3, 23, 31)).astype(np.uint16)
+    img[1] = 0
+    mask = np.zeros((23, 31), np.int32)
+    mask[22, 30] = 77
+    res = hp.run(img, mask, keep_probs=True)
+    assert res.n_cells == 1 and int(res.counts.sum()) == 1
+    norm = orc.normalize(img, 0.3, 99.8)
+    assert (norm[1] == -1).all()
+    want, _, _ = orc.build_patches(norm, mask, [0, 1, 2])
+    ref = orc.make_vit("nerve_cell")
+    ref.load_state_dict(weights.random_vit_state("nerve_cell", seed=1))
+    assert np.abs(res.probs["nerve_cell"].cpu().numpy() - orc.vit_probs(ref, want)).max() < 1e-3
