@@ -317,6 +317,8 @@ def merge_votes(probs0, types0, probs1, types1, vote_rank, type_thresh, confiden
     label = torch.empty(n, dtype=torch.uint8, device=dev)
     conf = torch.empty(n, dtype=torch.float32, device=dev)
     counts = torch.zeros(18, dtype=torch.int64, device=dev)
+    if n == 0:
+        return label, conf, counts
     t0 = (C.c_int * len(types0))(*types0)
     k1 = 0 if probs1 is None else probs1.shape[1]
     t1 = (C.c_int * max(k1, 1))(*(types1 or [0]))
