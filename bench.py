@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("RIBCA_PRECISION", "bf16x3"))
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2: 15-marker full panel -> vit_l (headline, BASELINE configs[1]); c3: 6-marker basic panel with "
+                         "CD11c missing -> MAE imputer + vit_s (configs[2], secondary)")
     return ap.parse_args()
 
 
@@ -93,10 +96,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_scene(size, seed, device):
+def make_scene(size, seed, device, channels=15):
     from multiplexed_image_annotator_b200 import synth
     mask = synth.synth_mask(size, size, grid=18, seed=seed, device=device)
-    img = synth.synth_image(mask, 15, seed=seed)
+    img = synth.synth_image(mask, channels, seed=seed)
     return img, mask
 
 
@@ -170,20 +173,29 @@ def main():
 
     # ---- workload: one synthetic scene per rank, host copy in pinned memory ----------------------------
     S = args.size
-    img_i32, mask_d = make_scene(S, 2 + rank, dev)
+    n_markers = 15 if args.workload == "c2" else 6
+    img_i32, mask_d = make_scene(S, 2 + rank, dev, n_markers)
     img_host = torch.from_numpy(synth.to_uint16(img_i32)).pin_memory()
     mask_host = mask_d.cpu().pin_memory()
     del img_i32
     img_dev = img_host.to(dev)
-    panel = "immune_full"
+    if args.workload == "c2":
+        panel, index, imputers = "immune_full", list(range(15)), {}
+    else:       # markers CD45,CD20,CD4,CD8,DAPI,CD3 -> immune_base index [0,1,2,3,4,-1,5], strict=False, infer=True
+        panel, index = "immune_base", [0, 1, 2, 3, 4, -1, 5]
+        mae = engine.MaeEngine(panel, weights.random_mae_state(panel, seed=7), dev, precision=args.precision)
+        imputers = {panel: (mae, [0, 1, 2, 3, 4, 6])}
+        args.no_cpu_baseline = True
     sd = weights.random_vit_state(panel, seed=7)
     eng = engine.VitEngine(panel, sd, dev, precision=args.precision, max_cells_per_call=args.chunk)
-    hp = HotPath({panel: list(range(15))}, {panel: eng}, chunk_cells=args.chunk, device=dev, shard_cells=False)
+    hp = HotPath({panel: index}, {panel: eng}, imputers, chunk_cells=args.chunk, device=dev, shard_cells=False)
     # head calibration: spread the label histogram of the random-init classifier
     warm = hp.run(img_dev, mask_d, to_host=False, keep_probs=True)
     n_cells = warm.n_cells
     norm = ops.normalize(img_dev, 0.3, 99.8)
-    (p256,), _, _ = ops.build_patches(norm, mask_d, ops.channel_min(norm), warm.cells, [list(range(15))], 0, min(256, n_cells))
+    (p256,), _, _ = ops.build_patches(norm, mask_d, ops.channel_min(norm), warm.cells, [index], 0, min(256, n_cells))
+    if imputers:
+        imputers[panel][0].impute(p256, imputers[panel][1])
     _, logits = eng.forward(p256, return_logits=True)
     sd_cal = weights.calibrate_head(sd, logits.mean(0).cpu().numpy(), 20.0)
     eng.set_head(sd_cal["head.weight"], sd_cal["head.bias"])
@@ -298,8 +310,11 @@ def main():
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"{args.precision} tensor-core passes, fp32 accumulate (stages 1-3 f32/f64 exact order)",
             "data": "synthetic",
-            "config": {"workload": f"C2: synthetic 15-marker {S}x{S} uint16 image + int32 mask per GPU, {n_cells} cells, "
-                                   f"immune_full panel -> vit_l (random-init, calibrated head), blur 0.3, amax 99.8, confidence 0.3",
+            "config": {"workload": (f"C2: synthetic 15-marker {S}x{S} uint16 image + int32 mask per GPU, {n_cells} cells, "
+                                    f"immune_full panel -> vit_l (random-init, calibrated head), blur 0.3, amax 99.8, confidence 0.3")
+                       if args.workload == "c2" else
+                       (f"C3: synthetic 6-marker {S}x{S} image (basic panel, CD11c missing), {n_cells} cells, strict=False infer=True "
+                        f"-> MAE imputer (L=7, keep 6) + vit_s, blur 0.3, amax 99.8, confidence 0.3"),
                        "cells_per_gpu": n_cells, "chunk_cells": args.chunk, "precision": args.precision,
                        "l2": f"inputs ({img_host.numel() * 2 / 1e6:.0f} MB image + {mask_host.numel() * 4 / 1e6:.0f} MB mask) exceed the 126 MB L2",
                        "parallelism": f"{world} x (one image per GPU), all-reduce of 18 counts"},
