@@ -174,6 +174,89 @@ attention_kernel(const float* __restrict__ qkv, int tokens, int heads, bf16* __r
   }
 }
 
+// Short sequences (the imputer: 7-16 tokens): several (cell, head) items per 128-thread CTA so that every
+// lane has a query row; thread = (item slot, row).  Same arithmetic as attention_kernel.
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_small_kernel(const float* __restrict__ qkv, int n_items, int tokens, int tpad, int heads,
+                       bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+  extern __shared__ float kv[];                   // per slot: K [tokens][HD], V [tokens][HD]
+  const int slots = 128 / tpad;
+  const int slot = threadIdx.x / tpad, t = threadIdx.x - slot * tpad;
+  const int item = blockIdx.x * slots + slot;
+  const int D = heads * HD;
+  constexpr int V4 = HD / 4;
+  float* Ks = kv + slot * 2 * tokens * HD;
+  float* Vs = Ks + tokens * HD;
+  const bool live = item < n_items && slot < slots;
+  const int cell = live ? item / heads : 0, head = live ? item - cell * heads : 0;
+  const float* base = qkv + (long long)cell * tokens * 3 * D;
+  if (live) {
+    for (int idx = t; idx < tokens * V4; idx += tpad) {
+      const int tt = idx / V4, d4 = idx - tt * V4;
+      const float4* rowp = reinterpret_cast<const float4*>(base + (long long)tt * 3 * D + head * HD);
+      reinterpret_cast<float4*>(Ks)[idx] = __ldg(rowp + (D >> 2) + d4);
+      reinterpret_cast<float4*>(Vs)[idx] = __ldg(rowp + 2 * (D >> 2) + d4);
+    }
+  }
+  __syncthreads();
+  if (!live || t >= tokens) return;
+  const float scale = 1.0f / sqrtf((float)HD);
+  float q[HD];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(base + (long long)t * 3 * D + head * HD);
+#pragma unroll
+    for (int d4 = 0; d4 < V4; ++d4) {
+      const float4 v = __ldg(qp + d4);
+      q[4 * d4] = v.x * scale; q[4 * d4 + 1] = v.y * scale; q[4 * d4 + 2] = v.z * scale; q[4 * d4 + 3] = v.w * scale;
+    }
+  }
+  float sc[16];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < tokens) {
+      const float4* kp = reinterpret_cast<const float4*>(Ks + j * HD);
+      float a = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < V4; ++d4) {
+        const float4 k = kp[d4];
+        a = fmaf(q[4 * d4], k.x, a); a = fmaf(q[4 * d4 + 1], k.y, a); a = fmaf(q[4 * d4 + 2], k.z, a); a = fmaf(q[4 * d4 + 3], k.w, a);
+      }
+      sc[j] = a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  float o[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+  float denom = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < tokens) {
+      const float p = expf(sc[j] - mx);
+      denom += p;
+      const float4* vp = reinterpret_cast<const float4*>(Vs + j * HD);
+#pragma unroll
+      for (int d4 = 0; d4 < V4; ++d4) {
+        const float4 v = vp[d4];
+        o[4 * d4] = fmaf(p, v.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(p, v.y, o[4 * d4 + 1]);
+        o[4 * d4 + 2] = fmaf(p, v.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(p, v.w, o[4 * d4 + 3]);
+      }
+    }
+  }
+  const float inv = 1.0f / denom;
+  const long long ob = ((long long)cell * tokens + t) * D + head * HD;
+#pragma unroll
+  for (int d4 = 0; d4 < V4; ++d4) {
+    uint32_t h[2], l[2];
+    split_bf16x2(o[4 * d4] * inv, o[4 * d4 + 1] * inv, h[0], l[0]);
+    split_bf16x2(o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv, h[1], l[1]);
+    *reinterpret_cast<uint2*>(o_hi + ob + 4 * d4) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(o_lo + ob + 4 * d4) = make_uint2(l[0], l[1]);
+  }
+}
+
 // ---- final LayerNorm on the class token + head + softmax --------------------------------------
 // one warp per cell (model.py:61-62 + timm forward_head + softmax(dim=1) of model.py:404)
 __global__ void __launch_bounds__(256)
@@ -311,6 +394,22 @@ int layernorm_launch(const float* x, int M, int D, const float* g, const float* 
 
 template <int HD>
 static int attention_launch_hd(const float* qkv, int cells, int tokens, int heads, bf16* hi, bf16* lo, cudaStream_t st) {
+  if (tokens <= 16) {       // packed short-sequence kernel
+    const int tpad = tokens <= 8 ? 8 : 16, slots = 128 / tpad, n_items = cells * heads;
+    const size_t smem_small = (size_t)slots * 2 * tokens * HD * sizeof(float);
+    static bool attr_small = false;
+    if (!attr_small) {
+      RIBCA_TRY(check_cuda(cudaFuncSetAttribute(attention_small_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 16 * HD * 4),
+                           "cudaFuncSetAttribute(attention_small_kernel)"));
+      attr_small = true;
+    }
+    const bool prof_s = profiling();
+    if (prof_s) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * HD, st);
+    attention_small_kernel<HD><<<(n_items + slots - 1) / slots, 128, smem_small, st>>>(qkv, n_items, tokens, tpad, heads, hi, lo);
+    if (prof_s) prof_end_span(st);
+    RIBCA_LAUNCH_CHECK("attention_small_kernel");
+    return RIBCA_OK;
+  }
   const size_t smem = (size_t)2 * tokens * HD * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {

@@ -149,7 +149,7 @@ class MaeEngine:
     """One panel's MAE marker imputer (reference markerImputer.py:69-329) resident on a CUDA device."""
 
     def __init__(self, spec: MaeSpec | str, state_dict: dict, device="cuda", precision: str = "bf16x3",
-                 max_cells_per_call: int = 2048):
+                 max_cells_per_call: int = 8192):
         self.spec = MAE_SPECS[spec] if isinstance(spec, str) else spec
         self.device = torch.device(device)
         if self.device.type != "cuda":
