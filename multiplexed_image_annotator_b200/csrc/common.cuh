@@ -12,6 +12,7 @@ namespace ribca {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+int ensure_dynamic_smem(const void* func, int bytes, const char* name);
 bool profiling();
 void prof_begin_span(int cls, double work, cudaStream_t st);
 void prof_end_span(cudaStream_t st);

@@ -2,6 +2,9 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 namespace ribca {
@@ -18,22 +21,40 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per (kernel, device): the attribute
+// belongs to the device's context, and several host threads may drive different streams.
+int ensure_dynamic_smem(const void* func, int bytes, const char* name) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  RIBCA_TRY(check_cuda(cudaGetDevice(&dev), "cudaGetDevice"));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({func, dev})) return RIBCA_OK;
+  RIBCA_TRY(check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), name));
+  done.insert({func, dev});
+  return RIBCA_OK;
+}
+
 // ---- optional per-kernel-class timing (bench.py's roofline leg) ----------------------------------
 // When enabled, the launch helpers of the dominant kernels bracket each launch with CUDA events on
 // the launching stream; ribca_profile_end() synchronises and sums the elapsed times per class.
 struct ProfSpan { int cls; cudaEvent_t a, b; double work; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfSpan> g_spans;
+static std::mutex g_prof_mu;
 
-bool profiling() { return g_prof_on; }
+bool profiling() { return g_prof_on.load(std::memory_order_relaxed); }
 
+// (profiling is a single-stream measurement aid: spans do not nest and are closed in issue order)
 void prof_begin_span(int cls, double work, cudaStream_t st) {
   ProfSpan s{cls, nullptr, nullptr, work};
   if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
   cudaEventRecord(s.a, st);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   g_spans.push_back(s);
 }
 void prof_end_span(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_spans.empty()) cudaEventRecord(g_spans.back().b, st);
 }
 
@@ -46,13 +67,14 @@ int ribca_version(void) { return 100; }
 long long ribca_launch_count(void) { return ribca::g_launches.load(std::memory_order_relaxed); }
 
 int ribca_profile_begin(void) {
-  ribca::g_spans.clear();
+  { std::lock_guard<std::mutex> lock(ribca::g_prof_mu); ribca::g_spans.clear(); }
   ribca::g_prof_on = true;
   return RIBCA_OK;
 }
 
 int ribca_profile_end(double* ms, long long* launches, double* work, int n_classes) {
   ribca::g_prof_on = false;
+  std::lock_guard<std::mutex> lock(ribca::g_prof_mu);
   for (int c = 0; c < n_classes; ++c) { ms[c] = 0.0; launches[c] = 0; work[c] = 0.0; }
   int rc = RIBCA_OK;
   for (auto& s : ribca::g_spans) {

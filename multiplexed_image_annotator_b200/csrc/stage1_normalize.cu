@@ -296,13 +296,7 @@ static int launch_fir(const Tin* in, const Traw* raw, float* out, int H, int W, 
   dim3 grid((nF + kOutF - 1) / kOutF, (nL + kOutL - 1) / kOutL);
   size_t smem = (size_t)(kOutF + 2 * taps.r) * kPitch * sizeof(double);
   auto kern = fir_kernel<Tin, Traw, HORIZ, EPI, STATS>;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)((kOutF + 2 * RIBCA_MAX_TAPS) * kPitch * sizeof(double))),
-                         "cudaFuncSetAttribute(fir_kernel)"));
-    attr_set = true;
-  }
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)((int)((kOutF + 2 * RIBCA_MAX_TAPS) * kPitch * sizeof(double))), "cudaFuncSetAttribute(fir_kernel)"));
   kern<<<grid, kFirThreads, smem, stream>>>(in, raw, out, H, W, taps, st);
   RIBCA_LAUNCH_CHECK("fir_kernel");
   return RIBCA_OK;

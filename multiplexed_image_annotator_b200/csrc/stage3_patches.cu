@@ -591,12 +591,7 @@ int ribca_build_patches_resized(const float* img, const int32_t* mask, int C_img
   for (int k = 0; k <= r_aa && k < 8; ++k) rz.w_aa[k] = h_w_aa[k];
   const size_t n = (size_t)patch_edge * patch_edge;
   const size_t smem = n * (8 + 8 + 4 + 1 + 1) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(build_patches_resized_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)((size_t)kMaxPW * kMaxPW * 22 + 16)), "cudaFuncSetAttribute(build_patches_resized_kernel)"));
-    attr_set = true;
-  }
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(build_patches_resized_kernel), (int)((int)((size_t)kMaxPW * kMaxPW * 22 + 16)), "cudaFuncSetAttribute(build_patches_resized_kernel)"));
   build_patches_resized_kernel<<<n_cells, kThreadsR, smem, as_stream(stream)>>>(img, mask, C_img, H, W, min_val, ids, cbbox, cell_begin,
                                                                                 n_cells, prm, rz, avg_int, windows);
   RIBCA_LAUNCH_CHECK("build_patches_resized_kernel");

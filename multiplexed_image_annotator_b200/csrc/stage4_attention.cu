@@ -297,12 +297,7 @@ template <int TP>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const AttnParams& p, bf16* hi, bf16* lo,
                      cudaStream_t st) {
   constexpr int kAttSmemBytes = att_smem_bytes(TP);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(attention_tc_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes),
-                         "cudaFuncSetAttribute(attention_tc_kernel)"));
-    attr_set = true;
-  }
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<TP>), (int)(kAttSmemBytes), "cudaFuncSetAttribute(attention_tc_kernel)"));
   const int grid = std::min(p.cells * p.heads, num_sms());
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)p.cells * p.heads * (double)p.tokens * p.tokens * p.hd, st);

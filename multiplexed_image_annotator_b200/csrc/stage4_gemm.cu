@@ -461,12 +461,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   epi.chunk = shp.BN % 32 == 0 ? 32 : 16;
   RIBCA_REQUIRE(!split_out || (out_plane * 2) % 16 == 0, "gemm: split output plane stride must be 16-byte aligned");
   RIBCA_TRY(make_output_map(&map_out, split_out, split_out ? out_split : (void*)out_f32, out_plane, M, N, epi.chunk));
-  static bool attr_set = false;
-  if (!attr_set) {
-    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
-                         "cudaFuncSetAttribute(gemm_tcgen05_kernel)"));
-    attr_set = true;
-  }
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel), (int)(kSmemBytes), "cudaFuncSetAttribute(gemm_tcgen05_kernel)"));
   const int n_pairs = (((M + BM - 1) / BM + 1) / 2) * (N / shp.BN);
   const int grid = 2 * std::min(n_pairs, num_sms() / 2);
   const bool prof = profiling();

@@ -397,12 +397,7 @@ static int attention_launch_hd(const float* qkv, int cells, int tokens, int head
   if (tokens <= 16) {       // packed short-sequence kernel
     const int tpad = tokens <= 8 ? 8 : 16, slots = 128 / tpad, n_items = cells * heads;
     const size_t smem_small = (size_t)slots * 2 * tokens * HD * sizeof(float);
-    static bool attr_small = false;
-    if (!attr_small) {
-      RIBCA_TRY(check_cuda(cudaFuncSetAttribute(attention_small_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 16 * HD * 4),
-                           "cudaFuncSetAttribute(attention_small_kernel)"));
-      attr_small = true;
-    }
+    RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_small_kernel<HD>), (int)(16 * 2 * 16 * HD * 4), "cudaFuncSetAttribute(attention_small_kernel)"));
     const bool prof_s = profiling();
     if (prof_s) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * HD, st);
     attention_small_kernel<HD><<<(n_items + slots - 1) / slots, 128, smem_small, st>>>(qkv, n_items, tokens, tpad, heads, hi, lo);
@@ -411,12 +406,7 @@ static int attention_launch_hd(const float* qkv, int cells, int tokens, int head
     return RIBCA_OK;
   }
   const size_t smem = (size_t)2 * tokens * HD * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RIBCA_TRY(check_cuda(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * HD * 4),
-                         "cudaFuncSetAttribute(attention_kernel)"));
-    attr_set = true;
-  }
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<HD>), (int)(2 * 128 * HD * 4), "cudaFuncSetAttribute(attention_kernel)"));
   const int threads = (tokens + 31) / 32 * 32;
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * HD, st);
