@@ -254,6 +254,11 @@ int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_cl
                       const int* h_vote_rank, const float* h_type_thresh, float confidence,
                       uint8_t* label, float* conf, long long* counts, ribca_stream_t stream);
 
+/* Per-pixel map from per-cell values (label / colour / confidence maps of Annotator.colorize,
+ * cta/model.py:806-858): out[p*channels + c] = mask[p] > 0 ? cell_value[id_to_index[mask[p]]*channels + c] : 0. */
+int ribca_paint_cells(const int32_t* mask, long long n_pixels, const int32_t* id_to_index, int max_id,
+                      const uint8_t* cell_value, int channels, uint8_t* out, ribca_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,7 @@ SIGNATURES = {
     "ribca_vit_forward": (_I, [C.POINTER(VitDesc), _P, _P, _P, _I, _P, _P, _P, _SZ, _I, _P]),
     "ribca_mae_workspace_bytes": (_SZ, [C.POINTER(MaeDesc), _I]),
     "ribca_mae_impute": (_I, [C.POINTER(MaeDesc), _P, _P, _P, _I, C.POINTER(_I), _I, _P, _SZ, _I, _P]),
+    "ribca_paint_cells": (_I, [_P, _LL, _P, _I, _P, _I, _P, _P]),
     "ribca_merge_votes": (_I, [_P, _I, C.POINTER(_I), _P, _I, C.POINTER(_I), _I, C.POINTER(_I), C.POINTER(_F), _F,
                                _P, _P, _P, _P]),
 }

@@ -292,11 +292,32 @@ class Annotator(object):
         self._skipped("tissue_region_analysis")
 
     def colorize(self, from_script=False):
-        if len(self.preprocessor.masks) == 0:
+        """reference model.py:806-858: colourised label map, confidence map and (GUI runs) the uint8 label
+        map `output_img.png` the Napari widget loads; painted on the device from the per-cell results.
+        Tissue-region maps are not produced (spatial statistics are outside the hot path)."""
+        from PIL import Image
+        from .utils import number_to_rgb
+        pre = self.preprocessor
+        if len(pre.masks) == 0:
             raise ValueError("No masks to colorize")
         if len(self.annotations) == 0:
             raise ValueError("No annotations to colorize")
-        self._skipped("colorize")
+        dev = pre.device
+        for i in range(len(pre.masks)):
+            type_of_all = np.array([int(np.where(self.cell_types == t)[0][0]) if t in self.cell_types else 0 for t in ALL_TYPES])
+            idx = torch.from_numpy(type_of_all[self.labels_index[i]].astype(np.uint8)).to(dev)           # index into cell_types
+            rgb = torch.tensor(self.colors, dtype=torch.uint8, device=dev)[idx.long()]
+            conf = [number_to_rgb(c) if c > 0 else [192, 192, 192] for c in self.confidence[i]]
+            conf = torch.tensor(conf, dtype=torch.uint8, device=dev).reshape(-1, 3)
+            m, cells = pre.masks_dev[i], pre.cells[i]
+            Image.fromarray(ops.paint_cells(m, cells, rgb.contiguous()).cpu().numpy()).save(
+                os.path.join(self.result_dir, f"{self.batch_id}_colorized_annotation_{i}.png"))
+            Image.fromarray(ops.paint_cells(m, cells, conf.contiguous()).cpu().numpy()).save(
+                os.path.join(self.result_dir, f"{self.batch_id}_confidence_{i}.png"))
+            if not from_script:
+                gui_dir = "./src/multiplexed_image_annotator/cell_type_annotation/_working_dir_temp"
+                if os.path.isdir(gui_dir):
+                    Image.fromarray(ops.paint_cells(m, cells, (idx + 1).contiguous()).cpu().numpy()).save(os.path.join(gui_dir, "output_img.png"))
 
     def umap_visualization(self):
         self._skipped("umap_visualization")

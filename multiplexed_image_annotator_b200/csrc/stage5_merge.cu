@@ -87,9 +87,33 @@ merge_votes_kernel(const float* __restrict__ p0, const float* __restrict__ p1, i
     atomicAdd(reinterpret_cast<unsigned long long*>(counts) + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
 }
 
+// per-pixel maps from per-cell values: out[p] = mask[p] > 0 ? value[id_to_index[mask[p]]] : 0
+// (the gather behind Annotator.colorize, reference cta/model.py:806-858, without per-cell pixel lists)
+__global__ void __launch_bounds__(256)
+paint_cells_kernel(const int32_t* __restrict__ mask, long long n, const int32_t* __restrict__ id_to_index, int max_id,
+                   const uint8_t* __restrict__ value, int channels, uint8_t* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int id = __ldg(mask + i);
+    int k = -1;
+    if (id > 0 && id <= max_id) k = __ldg(id_to_index + id);
+    for (int c = 0; c < channels; ++c) out[i * channels + c] = k >= 0 ? __ldg(value + (long long)k * channels + c) : (uint8_t)0;
+  }
+}
+
 }  // namespace ribca
 
 using namespace ribca;
+
+extern "C" int ribca_paint_cells(const int32_t* mask, long long n_pixels, const int32_t* id_to_index, int max_id,
+                                 const uint8_t* cell_value, int channels, uint8_t* out, ribca_stream_t stream) {
+  RIBCA_REQUIRE(mask && id_to_index && cell_value && out && n_pixels > 0 && channels > 0 && channels <= 4,
+                "ribca_paint_cells: bad arguments");
+  const int blocks = (int)std::min<long long>((n_pixels + 255) / 256, (long long)num_sms() * 16);
+  paint_cells_kernel<<<blocks, 256, 0, as_stream(stream)>>>(mask, n_pixels, id_to_index, max_id, cell_value, channels, out);
+  RIBCA_LAUNCH_CHECK("paint_cells_kernel");
+  return RIBCA_OK;
+}
 
 extern "C" int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_class0,
                                  const float* probs1, int classes1, const int* h_type_of_class1, int n_cells,

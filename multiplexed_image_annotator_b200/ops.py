@@ -327,3 +327,16 @@ def merge_votes(probs0, types0, probs1, types1, vote_rank, type_thresh, confiden
     _lib.check(_lib.lib().ribca_merge_votes(_ptr(probs0), k0, t0, _ptr(probs1), k1, t1, n, vr, tt, float(confidence),
                                             _ptr(label), _ptr(conf), _ptr(counts), _stream()), "ribca_merge_votes")
     return label, conf, counts
+
+
+def paint_cells(mask: torch.Tensor, cells: CellTable, cell_value: torch.Tensor) -> torch.Tensor:
+    """Per-pixel map from per-cell uint8 values (n,) or (n, channels<=4): 0 on the background."""
+    _need_cuda(mask, cell_value)
+    ch = 1 if cell_value.dim() == 1 else cell_value.shape[1]
+    h, w = mask.shape
+    out = torch.empty((h, w) if cell_value.dim() == 1 else (h, w, ch), dtype=torch.uint8, device=mask.device)
+    if cells.n == 0:
+        return out.zero_()
+    _lib.check(_lib.lib().ribca_paint_cells(_ptr(mask), mask.numel(), _ptr(cells.id_to_index), cells.max_id, _ptr(cell_value), ch,
+                                            _ptr(out), _stream()), "ribca_paint_cells")
+    return out

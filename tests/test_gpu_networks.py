@@ -249,5 +249,17 @@ def test_annotator_end_to_end_golden(golden_dir, tag, strict, tmp_path, monkeypa
         assert abs(float(fa[2]) - float(fb[2])) <= 1.001e-3
     comp = ann.cell_type_composition(reduction=False)[0]
     assert sum(comp.values()) == len(ann.annotations[0])
+    # colourised label map painted on the device: background 0, every pixel of a cell = its type colour
+    from PIL import Image
+    ann.colorize(from_script=True)
+    rgb = np.array(Image.open("results/g_colorized_annotation_0.png"))
+    mask = g[tag + "_mask"]
+    assert rgb.shape == mask.shape + (3,) and (rgb[mask == 0] == 0).all()
+    pos = ann.preprocessor.cell_pos_dict[0]
+    for j, key in enumerate(list(pos)[:10]):
+        rows, cols = pos[key]
+        t = int(np.where(ann.cell_types == ann.annotations[0][j])[0][0])
+        assert (rgb[rows, cols] == np.array(ann.colors[t], dtype=np.uint8)).all()
+        assert (rows, cols) == tuple(a.tolist() for a in np.nonzero(mask == key))
     ann.clear_tmp()
     assert not os.path.exists("tmp")

@@ -9,8 +9,8 @@ $SMALL > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$tag.csv $SMALL > gpurun_out/ncu_list_$tag.log 2>&1
 echo "ncu list exit $?"
 $SMALL > gpurun_out/plain2_$tag.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 50 -c 4 -o gpurun_out/prof_gemm_$tag -f $SMALL > gpurun_out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 1 -c 4 -o gpurun_out/prof_gemm_$tag -f $SMALL > gpurun_out/ncu_full_$tag.log 2>&1
 echo "ncu gemm exit $?"
 $SMALL > gpurun_out/plain3_$tag.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 14 -c 2 -o gpurun_out/prof_attn_$tag -f $SMALL > gpurun_out/ncu_attn_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 2 -c 2 -o gpurun_out/prof_attn_$tag -f $SMALL > gpurun_out/ncu_attn_$tag.log 2>&1
 echo "ncu attn exit $?"
