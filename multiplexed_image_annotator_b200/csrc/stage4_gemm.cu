@@ -40,7 +40,7 @@ namespace ribca {
 constexpr int BM = 128;
 constexpr int BK = 32;              // 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int kEpiWarps = 8;        // two per TMEM lane quadrant, alternating column chunks
 constexpr int kMaxBN = 256;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
@@ -48,7 +48,8 @@ constexpr int kATile = BM * BK * 2;             // one plane of A:  8 KB
 constexpr int kABytes = 2 * kATile;             // hi + lo:        16 KB
 constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, hi + lo: 16 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kStagingBytes = 4096;           // per epilogue warp: 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo)
+constexpr int kStagingTile = 4096;            // 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo tiles)
+constexpr int kStagingBytes = 2 * kStagingTile; // per epilogue warp, double-buffered: a store drains while the next chunk is computed
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
 
@@ -94,8 +95,8 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   const int cta_rank = (int)cluster_ctarank();
   const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
   const int half = (warp - 2) >> 2;                      // which of the two warps of the quadrant
-  uint8_t* stg = staging_base + (warp - 2) * kStagingBytes;
-  const uint32_t stg_addr = smem_u32(stg);
+  uint8_t* stg_base = staging_base + (warp - 2) * kStagingBytes;
+  int stg_sel = 0;
   const bool split_out = epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT;
   const int n_chunks = BN / CW;
   int local = 0;
@@ -111,6 +112,9 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
     for (int j = half; j < n_chunks; j += 2) {
       const int c = j * CW;
       const int col = n0 + c;
+      uint8_t* stg = stg_base + stg_sel * kStagingTile;
+      const uint32_t stg_addr = smem_u32(stg);
+      stg_sel ^= 1;
       float v[CW];
 #pragma unroll
       for (int q = 0; q < CW / 16; ++q) tmem_ld16_nowait(t_row + (uint32_t)(c + 16 * q), reinterpret_cast<uint32_t*>(v) + 16 * q);
@@ -139,8 +143,8 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
         uint32_t hi[CW / 2], lo[CW / 2];
 #pragma unroll
         for (int e = 0; e < CW / 2; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-        // all the math is done: only now wait until the previous bulk store has finished READING the staging tile
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // all the math is done: only now make sure the store issued from THIS buffer two chunks ago has been read
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch) {
@@ -150,7 +154,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
           *reinterpret_cast<uint4*>(stg + 32 * kRowB + off) = make_uint4(lo[4 * ch], lo[4 * ch + 1], lo[4 * ch + 2], lo[4 * ch + 3]);
         }
       } else {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
         constexpr int kRowB = CW * 4, kChunks = kRowB / 16;
 #pragma unroll
