@@ -75,13 +75,14 @@ struct GemmShape {
 // main loop: ~14 instructions instead of ~30 for erff.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));      // exp(-ax^2)
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  const float erf_abs = fmaf(-poly, __expf(-ax * ax), 1.0f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-// ---------------------------------------------------------------------------------------------
 // ---- epilogue: TMEM -> registers -> swizzled staging -> TMA store / reduce-add -----------------------
 // CW columns per step.  fp32 outputs: staging rows of CW*4 bytes (128B swizzle for CW = 32, 64B for 16);
 // split outputs: hi tile then lo tile, rows of CW*2 bytes (64B swizzle for CW = 32, 32B for 16).
