@@ -47,8 +47,13 @@ enum ribca_dtype { RIBCA_U8 = 0, RIBCA_U16 = 1, RIBCA_F32 = 2, RIBCA_I32 = 3 };
 enum ribca_precision {
   RIBCA_BF16X3 = 0, /* split-bf16, 3 tcgen05 passes (hi*hi + lo*hi + hi*lo), fp32 accumulate: parity mode */
   RIBCA_BF16X1 = 1, /* single bf16 pass: throughput mode (outside the 1e-3 probability tolerance)          */
-  RIBCA_SIMT_FP32 = 2 /* same contraction on the FP32 pipe (debug cross-check, no tensor cores)             */
+  RIBCA_SIMT_FP32 = 2, /* same contraction on the FP32 pipe (debug cross-check, no tensor cores)            */
+  RIBCA_F16F8 = 3   /* fp16 main pass + one e4m3 pass over a doubled K axis that carries both first-order
+                       correction terms (a_lo*w_hi + a_hi*w_lo): two passes' worth of tensor time, relative
+                       error ~2^-15 per product (measured max |dprob| 1.3e-4): default                    */
 };
+/* 16-bit operand plane formats (see csrc/common.cuh) */
+enum ribca_plane_format { RIBCA_PLANES_BF16 = 0, RIBCA_PLANES_F16F8 = 1 };
 
 const char* ribca_last_error(void);
 int ribca_version(void);
@@ -172,21 +177,32 @@ enum ribca_epilogue { RIBCA_EPI_STORE = 0, RIBCA_EPI_RESIDUAL = 1, RIBCA_EPI_GEL
 int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long long w_plane,
                          int M, int N, int K, const float* bias, const float* row_table,
                          int table_period, int epilogue, float* out_f32, void* out_split,
-                         long long out_plane, int precision, ribca_stream_t stream);
+                         long long out_plane, int precision, int w_log2_scale, ribca_stream_t stream);
+/* With precision RIBCA_F16F8 the operands are RIBCA_PLANES_F16F8 planes: plane 0 = fp16, plane 1 = two
+ * e4m3 per element; W is packed in the W role with scale 2^t (ribca_split_planes) and w_log2_scale = t + 8
+ * (the accumulator is multiplied by 2^-w_log2_scale).  A RIBCA_EPI_GELU output is written in the same
+ * format (it feeds the next GEMM); a RIBCA_EPI_STORE_SPLIT output stays bf16 {hi, lo} (it feeds attention).
+ * w_log2_scale is ignored by the other precisions. */
 /* x (fp32, n) -> bf16 planes hi / lo */
 int ribca_split_bf16(const float* x, long long n, void* hi, void* lo, ribca_stream_t stream);
+/* x (fp32, n even) -> two 16-bit planes in `format` (ribca_plane_format); w_role != 0 packs a weight matrix
+ * scaled by 2^log2_scale (RIBCA_PLANES_F16F8 only; see csrc/common.cuh for the exact encoding) */
+int ribca_split_planes(const float* x, long long n, int format, int w_role, int log2_scale,
+                       void* plane0, void* plane1, ribca_stream_t stream);
 
 /* row LayerNorm(eps) of x[M][D] -> split-bf16 planes (plane stride out_plane elements) */
 int ribca_layernorm_split(const float* x, int M, int D, const float* gamma, const float* beta,
-                          float eps, void* out_split, long long out_plane, ribca_stream_t stream);
+                          float eps, void* out_split, long long out_plane, int format,
+                          ribca_stream_t stream);
 /* multi-head self-attention over qkv[cells][tokens][3][heads][hd] (fp32) -> split-bf16 [M][D];
  * FP32-pipe kernel, used for the short sequences of the imputer (tokens <= 32) */
 int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head_dim,
-                    void* out_split, long long out_plane, ribca_stream_t stream);
+                    void* out_split, long long out_plane, int format, ribca_stream_t stream);
 /* the same on the tensor cores (tcgen05, split-bf16 passes) for tokens <= 112: qkv_split is
  * [2][M][3][heads][hdp] bf16 with hdp = head_dim rounded up to 16 and exact zeros in the padding */
 int ribca_attention_tc(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads,
-                       int head_dim, void* out_split, long long out_plane, ribca_stream_t stream);
+                       int head_dim, void* out_split, long long out_plane, int format,
+                       ribca_stream_t stream);
 
 /* Classifier: device-resident weights in the layout produced by the host packer
  * (multiplexed_image_annotator_b200/engine.py: pack_vit); all offsets in `desc` are element
@@ -201,6 +217,8 @@ typedef struct ribca_block_desc {
 
 typedef struct ribca_vit_desc {
   int dim, heads, depth, in_chans, classes, tokens;  /* tokens = 101 */
+  int plane_format;                                  /* ribca_plane_format of wsplit */
+  int w_log2_scale;                                  /* RIBCA_PLANES_F16F8: t + 8 (weights packed with scale 2^t) */
   long long split_plane;                             /* elements between the hi and lo plane */
   long long embed_w;                                 /* wsplit [dim][16*in_chans] */
   long long embed_table;                             /* wf32 [tokens][dim]: row0 = cls+pos0, row t = bias+pos_t */
@@ -217,6 +235,7 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
 typedef struct ribca_mae_desc {
   int channels;                    /* L = grid rows * cols (7 / 10 / 15) */
   int enc_dim, enc_heads, enc_depth, dec_dim, dec_heads, dec_depth;
+  int plane_format, w_log2_scale;  /* as in ribca_vit_desc */
   long long split_plane;
   long long embed_w;               /* wsplit [enc_dim][1600] */
   long long embed_bias, cls_token, pos_embed;            /* wf32: [enc_dim], [enc_dim], [1+L][enc_dim] */

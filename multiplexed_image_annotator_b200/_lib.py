@@ -82,7 +82,8 @@ class BlockDesc(C.Structure):
 
 class VitDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("heads", C.c_int), ("depth", C.c_int), ("in_chans", C.c_int),
-                ("classes", C.c_int), ("tokens", C.c_int), ("split_plane", C.c_longlong),
+                ("classes", C.c_int), ("tokens", C.c_int), ("plane_format", C.c_int), ("w_log2_scale", C.c_int),
+                ("split_plane", C.c_longlong),
                 ("embed_w", C.c_longlong), ("embed_table", C.c_longlong), ("norm_g", C.c_longlong),
                 ("norm_b", C.c_longlong), ("head_w", C.c_longlong), ("head_b", C.c_longlong),
                 ("blocks", BlockDesc * 16)]
@@ -91,7 +92,7 @@ class VitDesc(C.Structure):
 class MaeDesc(C.Structure):
     _fields_ = [("channels", C.c_int), ("enc_dim", C.c_int), ("enc_heads", C.c_int), ("enc_depth", C.c_int),
                 ("dec_dim", C.c_int), ("dec_heads", C.c_int), ("dec_depth", C.c_int),
-                ("split_plane", C.c_longlong), ("embed_w", C.c_longlong), ("embed_bias", C.c_longlong),
+                ("plane_format", C.c_int), ("w_log2_scale", C.c_int), ("split_plane", C.c_longlong), ("embed_w", C.c_longlong), ("embed_bias", C.c_longlong),
                 ("cls_token", C.c_longlong), ("pos_embed", C.c_longlong), ("norm_g", C.c_longlong),
                 ("norm_b", C.c_longlong), ("dec_embed_w", C.c_longlong), ("dec_embed_b", C.c_longlong),
                 ("mask_token", C.c_longlong), ("dec_pos_embed", C.c_longlong), ("dec_norm_g", C.c_longlong),
@@ -119,11 +120,12 @@ SIGNATURES = {
                                  C.POINTER(_P), C.POINTER(_D), _P, _P, _P]),
     "ribca_build_patches_resized": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I),
                                          C.POINTER(_P), C.POINTER(_D), _I, C.POINTER(_I), C.POINTER(_D), _I, _P, _P, _P]),
-    "ribca_gemm_splitbf16": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _P, _I, _I, _P, _P, _LL, _I, _P]),
+    "ribca_gemm_splitbf16": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _P, _I, _I, _P, _P, _LL, _I, _I, _P]),
     "ribca_split_bf16": (_I, [_P, _LL, _P, _P, _P]),
-    "ribca_layernorm_split": (_I, [_P, _I, _I, _P, _P, _F, _P, _LL, _P]),
-    "ribca_attention": (_I, [_P, _I, _I, _I, _I, _P, _LL, _P]),
-    "ribca_attention_tc": (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _P]),
+    "ribca_split_planes": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
+    "ribca_layernorm_split": (_I, [_P, _I, _I, _P, _P, _F, _P, _LL, _I, _P]),
+    "ribca_attention": (_I, [_P, _I, _I, _I, _I, _P, _LL, _I, _P]),
+    "ribca_attention_tc": (_I, [_P, _LL, _I, _I, _I, _I, _P, _LL, _I, _P]),
     "ribca_vit_workspace_bytes": (_SZ, [C.POINTER(VitDesc), _I]),
     "ribca_vit_forward": (_I, [C.POINTER(VitDesc), _P, _P, _P, _I, _P, _P, _P, _SZ, _I, _P]),
     "ribca_mae_workspace_bytes": (_SZ, [C.POINTER(MaeDesc), _I]),

@@ -137,7 +137,7 @@ class Annotator(object):
         os.makedirs(self.result_dir, exist_ok=True)
         self.cell_type_confidence = ({t: -1 for t in ALL_TYPES} if cell_type_confidence is None else cell_type_confidence)
         self.models = {}
-        self.precision = os.environ.get("RIBCA_PRECISION", "bf16x3")
+        self.precision = os.environ.get("RIBCA_PRECISION", ops.DEFAULT_PRECISION)
 
     # ---- stage 1-3 ---------------------------------------------------------------------------------
     def preprocess(self):

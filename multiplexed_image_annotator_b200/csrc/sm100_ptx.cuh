@@ -80,6 +80,15 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with e4m3 operands (kind::f8f6f4: K = 32 eight-bit elements per instruction, fp32 accumulate)
+__device__ __forceinline__ void umma_e4m3_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // commit of the pair's MMAs, arriving on the mbarrier at the same offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -176,6 +185,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_instr_desc(int m, int n, bool b_mn_major = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
+}
+// a/b format code 0: F16 for kind::f16 and E4M3 for kind::f8f6f4 - one descriptor serves both passes of the
+// f16f8 operand format
+__device__ __forceinline__ uint32_t make_instr_desc_fmt0(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA / TMA reads)

@@ -33,6 +33,7 @@ __host__ __device__ constexpr int att_smem_bytes(int tp) { return 2 * att_slot_b
 struct AttnParams {
   int cells, tokens, heads, hd, hdp, D;
   float scale_log2e;                          // log2(e) / sqrt(head_dim)
+  int out_fmt;                                // plane format of O (the proj GEMM's A operand)
 };
 
 // MN-major (N contiguous) B operand in a 128B-swizzled tile whose rows are K indices:
@@ -232,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (ch * 8 < p.hd) {
               uint32_t h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) split_bf16x2(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, h[e], l[e]);
+              for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, p.out_fmt, h[e], l[e]);
               *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
             }
@@ -255,8 +256,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const int d = q4 * 4;
             if (d < p.hd) {
               uint32_t h[2], l[2];
-              split_bf16x2(o[d] * inv, o[d + 1] * inv, h[0], l[0]);
-              split_bf16x2(o[d + 2] * inv, o[d + 3] * inv, h[1], l[1]);
+              split_pair(o[d] * inv, o[d + 1] * inv, p.out_fmt, h[0], l[0]);
+              split_pair(o[d + 2] * inv, o[d + 3] * inv, p.out_fmt, h[1], l[1]);
               *reinterpret_cast<uint2*>(out_hi + ob + d) = make_uint2(h[0], h[1]);
               *reinterpret_cast<uint2*>(out_lo + ob + d) = make_uint2(l[0], l[1]);
             }
@@ -309,13 +310,15 @@ static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtens
 
 // qkv_split: [2][M][3*heads*hdp] bf16, plane stride qkv_plane elements; out_split [2][M][heads*hd]
 int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads, int hd,
-                        void* out_split, long long out_plane, cudaStream_t st) {
+                        void* out_split, long long out_plane, int out_fmt, cudaStream_t st) {
+  RIBCA_REQUIRE(out_fmt == kFmtBf16 || out_fmt == kFmtF16F8, "attention_tc: unknown plane format %d", out_fmt);
   RIBCA_REQUIRE(tokens > 0 && tokens <= 112, "attention_tc: tokens=%d outside [1,112]", tokens);
   RIBCA_REQUIRE(hd > 0 && hd <= 64 && hd % 4 == 0, "attention_tc: head_dim=%d unsupported", hd);
   if (cells <= 0) return RIBCA_OK;
   AttnParams p;
   p.cells = cells; p.tokens = tokens; p.heads = heads; p.hd = hd; p.hdp = (hd + 15) / 16 * 16; p.D = heads * hd;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
+  p.out_fmt = out_fmt;
   const int width = 3 * heads * p.hdp;
   const long long M = (long long)cells * tokens;
   constexpr int TP = 112;
@@ -342,8 +345,9 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
 }  // namespace ribca
 
 extern "C" int ribca_attention_tc(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads,
-                                  int head_dim, void* out_split, long long out_plane, ribca_stream_t stream) {
+                                  int head_dim, void* out_split, long long out_plane, int format,
+                                  ribca_stream_t stream) {
   RIBCA_REQUIRE(qkv_split && out_split && heads > 0, "ribca_attention_tc: bad arguments");
-  return ribca::attention_tc_launch(qkv_split, qkv_plane, cells, tokens, heads, head_dim, out_split, out_plane,
+  return ribca::attention_tc_launch(qkv_split, qkv_plane, cells, tokens, heads, head_dim, out_split, out_plane, format,
                                     ribca::as_stream(stream));
 }

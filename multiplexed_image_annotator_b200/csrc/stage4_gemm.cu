@@ -40,8 +40,19 @@ namespace ribca {
 constexpr int BM = 128;
 constexpr int BK = 32;              // 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 5;
-constexpr int kEpiWarps = 8;        // two per TMEM lane quadrant, alternating column chunks
+#ifndef RIBCA_STAGES
+#define RIBCA_STAGES 6
+#endif
+constexpr int kStages = RIBCA_STAGES;
+#ifndef RIBCA_EPI_WARPS
+#define RIBCA_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = RIBCA_EPI_WARPS;   // kEpiWarps / 4 per TMEM lane quadrant, interleaved column chunks
+constexpr int kEpiPerQuad = kEpiWarps / 4;
+#ifndef RIBCA_STAGING_BUFS
+#define RIBCA_STAGING_BUFS 1
+#endif
+constexpr int kStagingBufs = RIBCA_STAGING_BUFS;      // per-warp staging tiles (shared memory budget: 1 with 12+ warps)
 constexpr int kMaxBN = 256;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr int kATile = BM * BK * 2;             // one plane of A:  8 KB
@@ -49,9 +60,11 @@ constexpr int kABytes = 2 * kATile;             // hi + lo:        16 KB
 constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, hi + lo: 16 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kStagingTile = 4096;            // 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo tiles)
-constexpr int kStagingBytes = 2 * kStagingTile; // per epilogue warp, double-buffered: a store drains while the next chunk is computed
+constexpr int kStagingBytes = kStagingBufs * kStagingTile; // per epilogue warp
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
+// (register allocation is per 4 warps: 14 warps -> 16 x 32 x 128 registers; 18 warps would be capped at 96)
+#define RIBCA_GEMM_BOUNDS __launch_bounds__(kGemmThreads, 1)
 
 struct GemmEpilogue {
   const float* bias;        // [N] or null
@@ -62,25 +75,30 @@ struct GemmEpilogue {
   float* out_f32;           // [M][N]          (SIMT path only; the tcgen05 path stores through tmap_out)
   __nv_bfloat16* out_hi;    // split output planes
   __nv_bfloat16* out_lo;
+  int out_fmt;              // plane format of a split output (kFmtBf16 / kFmtF16F8)
+  float acc_scale;          // accumulator scale (2^-(t+8) for f16f8 weights, else 1)
 };
 
 struct GemmShape {
   int M, N, K;
   int BN;                   // N tile (multiple of 16, <= 256, divides N)
-  int n_planes;             // 2 (bf16x3: hi and lo staged) or 1 (bf16x1: hi only)
+  int n_planes;             // 2 (bf16x3 / f16f8: both planes staged) or 1 (bf16x1: hi only)
+  int fmt;                  // operand plane format: kFmtBf16 or kFmtF16F8
 };
 
 // exact (erf) GELU of timm's Mlp.  erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7; measured GELU error
 // < 5e-7 absolute in fp32, far below the split-bf16 output quantum) so the fc1 epilogue stays under the
 // main loop: ~14 instructions instead of ~30 for erff.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
+  // a = |x| / sqrt(2) * sqrt(log2 e): exp(-(x/sqrt 2)^2) = 2^(-a^2); A-S's p is rescaled by 1 / sqrt(log2 e)
+  const float a = fabsf(x) * 0.84932180028801904272f;
   float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));      // exp(-ax^2)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, a, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * a));
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
   const float erf_abs = fmaf(-poly, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);               // 0.5 x (1 + sign(x) erf|x/sqrt 2|)
 }
 
 // ---- epilogue: TMEM -> registers -> swizzled staging -> TMA store / reduce-add -----------------------
@@ -95,7 +113,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   const int n_pairs = (((shp.M + BM - 1) / BM + 1) / 2) * n_tiles_n;
   const int cta_rank = (int)cluster_ctarank();
   const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
-  const int half = (warp - 2) >> 2;                      // which of the two warps of the quadrant
+  const int sub = (warp - 2) >> 2;                       // which of the warps of the quadrant
   uint8_t* stg_base = staging_base + (warp - 2) * kStagingBytes;
   int stg_sel = 0;
   const bool split_out = epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT;
@@ -110,58 +128,91 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
     mbar_wait(&tmem_full[buf], use & 1u);
     tcgen05_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
-    for (int j = half; j < n_chunks; j += 2) {
+    // the warps of a quadrant take interleaved column chunks; the starting warp rotates with the tile so that an
+    // uneven chunk count (8 chunks over 3 warps) evens out
+    int j0 = sub + local % kEpiPerQuad;
+    if (j0 >= kEpiPerQuad) j0 -= kEpiPerQuad;
+    for (int j = j0; j < n_chunks; j += kEpiPerQuad) {
       const int c = j * CW;
       const int col = n0 + c;
       uint8_t* stg = stg_base + stg_sel * kStagingTile;
       const uint32_t stg_addr = smem_u32(stg);
-      stg_sel ^= 1;
+      if (kStagingBufs == 2) stg_sel ^= 1;
       float v[CW];
 #pragma unroll
       for (int q = 0; q < CW / 16; ++q) tmem_ld16_nowait(t_row + (uint32_t)(c + 16 * q), reinterpret_cast<uint32_t*>(v) + 16 * q);
-      tmem_ld_wait();
+      // bias of this chunk: requested while the TMEM loads are in flight
+      float4 bv[CW / 4];
       if (epi.bias) {
 #pragma unroll
-        for (int q = 0; q < CW / 4; ++q) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q);
-          v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-        }
+        for (int q = 0; q < CW / 4; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q);
       }
-      if (table_row) {
+      tmem_ld_wait();
+      const float sc = epi.acc_scale;                       // 1 except for f16f8 weights (2^-(t+8))
+      // 16 columns at a time, each finished down to its shared-memory stores (short register live ranges)
 #pragma unroll
-        for (int q = 0; q < CW / 4; ++q) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(table_row + col) + q);
-          v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      for (int hh = 0; hh < CW / 16; ++hh) {
+        float* u = v + 16 * hh;
+        if (epi.bias) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = bv[4 * hh + q];
+            u[4 * q] = fmaf(u[4 * q], sc, b.x); u[4 * q + 1] = fmaf(u[4 * q + 1], sc, b.y);
+            u[4 * q + 2] = fmaf(u[4 * q + 2], sc, b.z); u[4 * q + 3] = fmaf(u[4 * q + 3], sc, b.w);
+          }
+        } else if (sc != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] *= sc;
         }
-      }
-      if (split_out) {
-        if (epi.mode == RIBCA_EPI_GELU) {
+        if (table_row) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] = gelu_erf(v[i]);
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(table_row + col + 16 * hh) + q);
+            u[4 * q] += b.x; u[4 * q + 1] += b.y; u[4 * q + 2] += b.z; u[4 * q + 3] += b.w;
+          }
         }
-        // rows of CW bf16 (CW*2 bytes); 16-byte chunk index XOR-swizzled like the TMA store expects
-        constexpr int kRowB = CW * 2, kChunks = kRowB / 16;
-        uint32_t hi[CW / 2], lo[CW / 2];
+        uint32_t hi[8], lo[8];
+        if (split_out) {
+          if (epi.mode == RIBCA_EPI_GELU) {
 #pragma unroll
-        for (int e = 0; e < CW / 2; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-        // all the math is done: only now make sure the store issued from THIS buffer two chunks ago has been read
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
+            for (int i = 0; i < 16; ++i) u[i] = gelu_erf(u[i]);
+          }
+          if (epi.out_fmt == kFmtF16F8) {
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-          const int sw = (CW == 32) ? (ch ^ ((lane >> 1) & 3)) : (ch ^ ((lane >> 2) & 1));   // SWIZZLE_64B / SWIZZLE_32B
-          const int off = lane * kRowB + (sw << 4);
-          *reinterpret_cast<uint4*>(stg + off) = make_uint4(hi[4 * ch], hi[4 * ch + 1], hi[4 * ch + 2], hi[4 * ch + 3]);
-          *reinterpret_cast<uint4*>(stg + 32 * kRowB + off) = make_uint4(lo[4 * ch], lo[4 * ch + 1], lo[4 * ch + 2], lo[4 * ch + 3]);
+            for (int e = 0; e < 8; ++e) split_f16f8_x2(u[2 * e], u[2 * e + 1], hi[e], lo[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16x2(u[2 * e], u[2 * e + 1], hi[e], lo[e]);
+          }
         }
-      } else {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        constexpr int kRowB = CW * 4, kChunks = kRowB / 16;
+        if (hh == 0) {
+          // the math of the first half is done: only now make sure the store issued from this staging buffer
+          // (kStagingBufs chunks ago) has been read
+          if (lane == 0) {
+            if (kStagingBufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          __syncwarp();
+        }
+        if (split_out) {
+          // rows of CW 16-bit elements (CW*2 bytes) per plane; 16-byte chunk index XOR-swizzled like the TMA store expects
+          constexpr int kRowB = CW * 2;
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-          const int sw = (CW == 32) ? (ch ^ (lane & 7)) : (ch ^ ((lane >> 1) & 3));           // SWIZZLE_128B / SWIZZLE_64B
-          *reinterpret_cast<float4*>(stg + lane * kRowB + (sw << 4)) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int ch = 2 * hh + c2;
+            const int sw = (CW == 32) ? (ch ^ ((lane >> 1) & 3)) : (ch ^ ((lane >> 2) & 1));   // SWIZZLE_64B / SWIZZLE_32B
+            const int off = lane * kRowB + (sw << 4);
+            *reinterpret_cast<uint4*>(stg + off) = make_uint4(hi[4 * c2], hi[4 * c2 + 1], hi[4 * c2 + 2], hi[4 * c2 + 3]);
+            *reinterpret_cast<uint4*>(stg + 32 * kRowB + off) = make_uint4(lo[4 * c2], lo[4 * c2 + 1], lo[4 * c2 + 2], lo[4 * c2 + 3]);
+          }
+        } else {
+          constexpr int kRowB = CW * 4;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int ch = 4 * hh + c4;
+            const int sw = (CW == 32) ? (ch ^ (lane & 7)) : (ch ^ ((lane >> 1) & 3));           // SWIZZLE_128B / SWIZZLE_64B
+            *reinterpret_cast<float4*>(stg + lane * kRowB + (sw << 4)) = make_float4(u[4 * c4], u[4 * c4 + 1], u[4 * c4 + 2], u[4 * c4 + 3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -189,7 +240,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   __syncwarp();
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) RIBCA_GEMM_BOUNDS
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmShape shp, const GemmEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
@@ -252,7 +303,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && leader) {
-      const uint32_t idesc = make_instr_desc(2 * BM, BN);
+      const uint32_t idesc = shp.fmt == kFmtF16F8 ? make_instr_desc_fmt0(2 * BM, BN) : make_instr_desc(2 * BM, BN);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int pr = pair0; pr < n_pairs; pr += pair_stride, ++local) {
@@ -266,7 +317,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
-          if (shp.n_planes == 2) {
+          if (shp.fmt == kFmtF16F8) {
+            // e4m3 pair planes (both correction terms, K doubled: 32 bytes = one K = 32 instruction per 16 elements)
+            // then the fp16 planes; one accumulator, one instruction descriptor (format code 0 = E4M3 = F16)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t a_0 = make_smem_desc_sw64(a_addr + k * UMMA_K * 2);
+              const uint64_t a_1 = make_smem_desc_sw64(a_addr + kATile + k * UMMA_K * 2);
+              const uint64_t w_0 = make_smem_desc_sw64(b_addr + k * UMMA_K * 2);
+              const uint64_t w_1 = make_smem_desc_sw64(b_addr + w_tile + k * UMMA_K * 2);
+              umma_e4m3_2sm(d_tmem, a_1, w_1, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, a_0, w_0, idesc, 1u);
+            }
+          } else if (shp.n_planes == 2) {
             // lo.hi + hi.lo + hi.hi from the four staged tiles
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -430,7 +493,7 @@ int pick_bn(int N) {
 
 int gemm_launch(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
                 const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
-                void* out_split, long long out_plane, int precision, cudaStream_t stream) {
+                void* out_split, long long out_plane, int precision, int w_log2_scale, cudaStream_t stream) {
   RIBCA_REQUIRE(A && W, "gemm: null operand");
   RIBCA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RIBCA_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm: N=%d must be a multiple of 16 and K=%d of 8", N, K);
@@ -446,20 +509,25 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   shp.BN = pick_bn(N);
   RIBCA_REQUIRE(shp.BN > 0, "gemm: no N tile for N=%d", N);
   shp.n_planes = precision == RIBCA_BF16X1 ? 1 : 2;
+  shp.fmt = precision == RIBCA_F16F8 ? kFmtF16F8 : kFmtBf16;
   GemmEpilogue epi;
   epi.bias = bias; epi.row_table = row_table; epi.table_period = table_period > 0 ? table_period : 1;
   epi.mode = epilogue; epi.out_f32 = out_f32; epi.chunk = 32;
   epi.out_hi = static_cast<__nv_bfloat16*>(out_split);
   epi.out_lo = out_split ? static_cast<__nv_bfloat16*>(out_split) + out_plane : nullptr;
+  // f16f8: a GELU output feeds the next GEMM (same format); a plain split store feeds attention (bf16 {hi, lo})
+  epi.out_fmt = (precision == RIBCA_F16F8 && epilogue == RIBCA_EPI_GELU) ? kFmtF16F8 : kFmtBf16;
+  RIBCA_REQUIRE(w_log2_scale > -64 && w_log2_scale < 64, "gemm: weight scale exponent %d out of range", w_log2_scale);
+  epi.acc_scale = precision == RIBCA_F16F8 ? ldexpf(1.0f, -w_log2_scale) : 1.0f;
 
-  if (precision == RIBCA_SIMT_FP32) {
+  if (precision == RIBCA_SIMT_FP32) {   // bf16 {hi, lo} planes only
     dim3 grid((N + ST - 1) / ST, (M + ST - 1) / ST);
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), a_plane,
                                                static_cast<const __nv_bfloat16*>(W), w_plane, shp, epi);
     RIBCA_LAUNCH_CHECK("gemm_simt_kernel");
     return RIBCA_OK;
   }
-  RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1, "gemm: unknown precision %d", precision);
+  RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1 || precision == RIBCA_F16F8, "gemm: unknown precision %d", precision);
   CUtensorMap map_a, map_w, map_out;
   RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
   RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN / 2, shp.n_planes));      // each CTA of a pair stages half of the W tile
@@ -474,6 +542,33 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, map_out, shp, epi);
   if (prof) prof_end_span(stream);
   RIBCA_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return RIBCA_OK;
+}
+
+// generic fp32 -> operand planes: A role (activations) or W role (weights scaled by 2^log2_scale, f16f8 only)
+__global__ void split_planes_kernel(const float* __restrict__ x, long long n_pairs, int fmt, int w_role, float sc,
+                                    uint32_t* __restrict__ p0, uint32_t* __restrict__ p1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+    const float2 v = reinterpret_cast<const float2*>(x)[i];
+    uint32_t a, b;
+    if (fmt == kFmtF16F8 && w_role) split_f16f8_w_x2(v.x, v.y, sc, a, b);
+    else split_pair(v.x, v.y, fmt, a, b);
+    p0[i] = a;
+    p1[i] = b;
+  }
+}
+
+int split_planes_launch(const float* x, long long n, int fmt, int w_role, int log2_scale, void* p0, void* p1, cudaStream_t stream) {
+  if (n <= 0) return RIBCA_OK;
+  RIBCA_REQUIRE(n % 2 == 0, "split_planes: element count %lld must be even", n);
+  RIBCA_REQUIRE(fmt == kFmtBf16 || fmt == kFmtF16F8, "split_planes: unknown format %d", fmt);
+  RIBCA_REQUIRE(log2_scale > -64 && log2_scale < 64, "split_planes: scale exponent %d out of range", log2_scale);
+  const long long pairs = n / 2;
+  int blocks = (int)std::min<long long>((pairs + 255) / 256, (long long)num_sms() * 8);
+  split_planes_kernel<<<blocks, 256, 0, stream>>>(x, pairs, fmt, w_role, ldexpf(1.0f, log2_scale), static_cast<uint32_t*>(p0),
+                                                  static_cast<uint32_t*>(p1));
+  RIBCA_LAUNCH_CHECK("split_planes_kernel");
   return RIBCA_OK;
 }
 
@@ -493,10 +588,16 @@ extern "C" {
 
 int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
                          const float* bias, const float* row_table, int table_period, int epilogue,
-                         float* out_f32, void* out_split, long long out_plane, int precision,
+                         float* out_f32, void* out_split, long long out_plane, int precision, int w_log2_scale,
                          ribca_stream_t stream) {
   return gemm_launch(A, a_plane, W, w_plane, M, N, K, bias, row_table, table_period, epilogue, out_f32, out_split,
-                     out_plane, precision, as_stream(stream));
+                     out_plane, precision, w_log2_scale, as_stream(stream));
+}
+
+int ribca_split_planes(const float* x, long long n, int format, int w_role, int log2_scale, void* plane0, void* plane1,
+                       ribca_stream_t stream) {
+  RIBCA_REQUIRE(x && plane0 && plane1, "ribca_split_planes: null pointer");
+  return split_planes_launch(x, n, format, w_role, log2_scale, plane0, plane1, as_stream(stream));
 }
 
 int ribca_split_bf16(const float* x, long long n, void* hi, void* lo, ribca_stream_t stream) {

@@ -12,17 +12,19 @@ namespace ribca {
 
 int gemm_launch(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
                 const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
-                void* out_split, long long out_plane, int precision, cudaStream_t stream);
+                void* out_split, long long out_plane, int precision, int w_log2_scale, cudaStream_t stream);
 
 int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads, int hd,
-                        void* out_split, long long out_plane, cudaStream_t st);
+                        void* out_split, long long out_plane, int out_fmt, cudaStream_t st);
+
+static inline int fmt_of(int precision) { return precision == RIBCA_F16F8 ? kFmtF16F8 : kFmtBf16; }
 
 typedef __nv_bfloat16 bf16;
 
 // ---- patches -> patch-embed A operand ---------------------------------------------------------
 // A[(cell*101 + 1 + py*10 + px)][c*16 + ky*4 + kx] = patch[cell][c][py*4+ky][px*4+kx]; row cell*101 = 0
 __global__ void __launch_bounds__(256)
-im2col_split_kernel(const float* __restrict__ patches, int n_cells, int C, bf16* __restrict__ a_hi,
+im2col_split_kernel(const float* __restrict__ patches, int n_cells, int C, int fmt, bf16* __restrict__ a_hi,
                     bf16* __restrict__ a_lo) {
   const int Kpe = 16 * C;
   const long long total = (long long)n_cells * C * 40 * 10;       // one float4 (4 kx) per thread
@@ -35,10 +37,11 @@ im2col_split_kernel(const float* __restrict__ patches, int n_cells, int C, bf16*
     const float4 v = __ldg(reinterpret_cast<const float4*>(patches) + t);
     const long long row = cell * 101 + 1 + (y >> 2) * 10 + px;
     const long long o = row * Kpe + c * 16 + (y & 3) * 4;
-    bf16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(a_hi + o) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(a_lo + o) = *reinterpret_cast<const uint2*>(l);
+    uint32_t h[2], l[2];
+    split_pair(v.x, v.y, fmt, h[0], l[0]);
+    split_pair(v.z, v.w, fmt, h[1], l[1]);
+    *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(l[0], l[1]);
   }
   // class-token rows are all-zero A rows (their value comes from the epilogue's row table)
   const long long ztotal = (long long)n_cells * Kpe;
@@ -54,7 +57,7 @@ im2col_split_kernel(const float* __restrict__ patches, int n_cells, int C, bf16*
 // one warp per row, D % 4 == 0, D <= 1024; fp32 two-pass statistics
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+                       const float* __restrict__ beta, float eps, int fmt, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nv = D >> 2;                          // float4 per row
@@ -84,14 +87,12 @@ layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* _
       if (idx < nv) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
         const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
-        bf16 h[4], l[4];
-        split_bf16((v[i].x - mean) * rstd * g.x + b.x, h[0], l[0]);
-        split_bf16((v[i].y - mean) * rstd * g.y + b.y, h[1], l[1]);
-        split_bf16((v[i].z - mean) * rstd * g.z + b.z, h[2], l[2]);
-        split_bf16((v[i].w - mean) * rstd * g.w + b.w, h[3], l[3]);
+        uint32_t h[2], l[2];
+        split_pair((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y, fmt, h[0], l[0]);
+        split_pair((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w, fmt, h[1], l[1]);
         const long long o = (long long)row * D + 4 * idx;
-        *reinterpret_cast<uint2*>(o_hi + o) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(o_lo + o) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(o_hi + o) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2*>(o_lo + o) = make_uint2(l[0], l[1]);
       }
     }
   }
@@ -102,7 +103,7 @@ layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* _
 // two passes over the keys (row max, then exp / sum / PV) keep the softmax in exact fp32.
 template <int HD>
 __global__ void __launch_bounds__(128)
-attention_kernel(const float* __restrict__ qkv, int tokens, int heads, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+attention_kernel(const float* __restrict__ qkv, int tokens, int heads, int fmt, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
   extern __shared__ float kv[];                   // K [tokens][HD], V [tokens][HD]
   float* Ks = kv;
   float* Vs = kv + tokens * HD;
@@ -166,11 +167,11 @@ attention_kernel(const float* __restrict__ qkv, int tokens, int heads, bf16* __r
   const long long ob = ((long long)cell * tokens + t) * D + head * HD;
 #pragma unroll
   for (int d4 = 0; d4 < V4; ++d4) {
-    bf16 h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) split_bf16(o[4 * d4 + e] * inv, h[e], l[e]);
-    *reinterpret_cast<uint2*>(o_hi + ob + 4 * d4) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(o_lo + ob + 4 * d4) = *reinterpret_cast<const uint2*>(l);
+    uint32_t h[2], l[2];
+    split_pair(o[4 * d4] * inv, o[4 * d4 + 1] * inv, fmt, h[0], l[0]);
+    split_pair(o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv, fmt, h[1], l[1]);
+    *reinterpret_cast<uint2*>(o_hi + ob + 4 * d4) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(o_lo + ob + 4 * d4) = make_uint2(l[0], l[1]);
   }
 }
 
@@ -178,7 +179,7 @@ attention_kernel(const float* __restrict__ qkv, int tokens, int heads, bf16* __r
 // lane has a query row; thread = (item slot, row).  Same arithmetic as attention_kernel.
 template <int HD>
 __global__ void __launch_bounds__(128)
-attention_small_kernel(const float* __restrict__ qkv, int n_items, int tokens, int tpad, int heads,
+attention_small_kernel(const float* __restrict__ qkv, int n_items, int tokens, int tpad, int heads, int fmt,
                        bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
   extern __shared__ float kv[];                   // per slot: K [tokens][HD], V [tokens][HD]
   const int slots = 128 / tpad;
@@ -250,8 +251,8 @@ attention_small_kernel(const float* __restrict__ qkv, int n_items, int tokens, i
 #pragma unroll
   for (int d4 = 0; d4 < V4; ++d4) {
     uint32_t h[2], l[2];
-    split_bf16x2(o[4 * d4] * inv, o[4 * d4 + 1] * inv, h[0], l[0]);
-    split_bf16x2(o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv, h[1], l[1]);
+    split_pair(o[4 * d4] * inv, o[4 * d4 + 1] * inv, fmt, h[0], l[0]);
+    split_pair(o[4 * d4 + 2] * inv, o[4 * d4 + 3] * inv, fmt, h[1], l[1]);
     *reinterpret_cast<uint2*>(o_hi + ob + 4 * d4) = make_uint2(h[0], h[1]);
     *reinterpret_cast<uint2*>(o_lo + ob + 4 * d4) = make_uint2(l[0], l[1]);
   }
@@ -304,7 +305,7 @@ struct PresentList { int n; int idx[RIBCA_MAX_PANEL_CH]; int rank[RIBCA_MAX_PANE
 // encoder A operand: row (cell, 0) = 0, row (cell, 1+i) = the 1600 pixels of channel present[i]
 __global__ void __launch_bounds__(256)
 mae_tiles_split_kernel(const float* __restrict__ patches, int n_cells, int L, const __grid_constant__ PresentList pl,
-                       bf16* __restrict__ a_hi, bf16* __restrict__ a_lo) {
+                       int fmt, bf16* __restrict__ a_hi, bf16* __restrict__ a_lo) {
   const int Te = pl.n + 1;
   const long long total = (long long)n_cells * Te * 400;          // float4 units
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -314,11 +315,12 @@ mae_tiles_split_kernel(const float* __restrict__ patches, int n_cells, int L, co
     const long long cell = t / (400ll * Te);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tok > 0) v = __ldg(reinterpret_cast<const float4*>(patches + (cell * L + pl.idx[tok - 1]) * 1600ll) + q);
-    bf16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    uint32_t h[2], l[2];
+    split_pair(v.x, v.y, fmt, h[0], l[0]);
+    split_pair(v.z, v.w, fmt, h[1], l[1]);
     const long long o = (cell * Te + tok) * 1600ll + 4 * q;
-    *reinterpret_cast<uint2*>(a_hi + o) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(a_lo + o) = *reinterpret_cast<const uint2*>(l);
+    *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(l[0], l[1]);
   }
 }
 
@@ -380,27 +382,27 @@ static int grid_for(long long work_items, int per_block) {
 }
 
 int layernorm_launch(const float* x, int M, int D, const float* g, const float* b, float eps, void* out_split,
-                     long long out_plane, cudaStream_t st) {
+                     long long out_plane, int fmt, cudaStream_t st) {
   RIBCA_REQUIRE(D % 4 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 4 and <= 1024", D);
   if (M <= 0) return RIBCA_OK;
   bf16* hi = static_cast<bf16*>(out_split);
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_LAYERNORM, (double)M * (double)D * 8.0, st);
-  layernorm_split_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, M, D, g, b, eps, hi, hi + out_plane);
+  layernorm_split_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, M, D, g, b, eps, fmt, hi, hi + out_plane);
   if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("layernorm_split_kernel");
   return RIBCA_OK;
 }
 
 template <int HD>
-static int attention_launch_hd(const float* qkv, int cells, int tokens, int heads, bf16* hi, bf16* lo, cudaStream_t st) {
+static int attention_launch_hd(const float* qkv, int cells, int tokens, int heads, int fmt, bf16* hi, bf16* lo, cudaStream_t st) {
   if (tokens <= 16) {       // packed short-sequence kernel
     const int tpad = tokens <= 8 ? 8 : 16, slots = 128 / tpad, n_items = cells * heads;
     const size_t smem_small = (size_t)slots * 2 * tokens * HD * sizeof(float);
     RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_small_kernel<HD>), (int)(16 * 2 * 16 * HD * 4), "cudaFuncSetAttribute(attention_small_kernel)"));
     const bool prof_s = profiling();
     if (prof_s) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * HD, st);
-    attention_small_kernel<HD><<<(n_items + slots - 1) / slots, 128, smem_small, st>>>(qkv, n_items, tokens, tpad, heads, hi, lo);
+    attention_small_kernel<HD><<<(n_items + slots - 1) / slots, 128, smem_small, st>>>(qkv, n_items, tokens, tpad, heads, fmt, hi, lo);
     if (prof_s) prof_end_span(st);
     RIBCA_LAUNCH_CHECK("attention_small_kernel");
     return RIBCA_OK;
@@ -410,24 +412,24 @@ static int attention_launch_hd(const float* qkv, int cells, int tokens, int head
   const int threads = (tokens + 31) / 32 * 32;
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * HD, st);
-  attention_kernel<HD><<<cells * heads, threads, smem, st>>>(qkv, tokens, heads, hi, lo);
+  attention_kernel<HD><<<cells * heads, threads, smem, st>>>(qkv, tokens, heads, fmt, hi, lo);
   if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("attention_kernel");
   return RIBCA_OK;
 }
 
 int attention_launch(const float* qkv, int cells, int tokens, int heads, int hd, void* out_split, long long out_plane,
-                     cudaStream_t st) {
+                     int fmt, cudaStream_t st) {
   RIBCA_REQUIRE(tokens > 0 && tokens <= 128, "attention: tokens=%d outside [1,128]", tokens);
   if (cells <= 0) return RIBCA_OK;
   bf16* hi = static_cast<bf16*>(out_split);
   bf16* lo = hi + out_plane;
   switch (hd) {
-    case 12: return attention_launch_hd<12>(qkv, cells, tokens, heads, hi, lo, st);
-    case 24: return attention_launch_hd<24>(qkv, cells, tokens, heads, hi, lo, st);
-    case 32: return attention_launch_hd<32>(qkv, cells, tokens, heads, hi, lo, st);
-    case 48: return attention_launch_hd<48>(qkv, cells, tokens, heads, hi, lo, st);
-    case 64: return attention_launch_hd<64>(qkv, cells, tokens, heads, hi, lo, st);
+    case 12: return attention_launch_hd<12>(qkv, cells, tokens, heads, fmt, hi, lo, st);
+    case 24: return attention_launch_hd<24>(qkv, cells, tokens, heads, fmt, hi, lo, st);
+    case 32: return attention_launch_hd<32>(qkv, cells, tokens, heads, fmt, hi, lo, st);
+    case 48: return attention_launch_hd<48>(qkv, cells, tokens, heads, fmt, hi, lo, st);
+    case 64: return attention_launch_hd<64>(qkv, cells, tokens, heads, fmt, hi, lo, st);
     default: set_error("attention: unsupported head_dim %d", hd); return RIBCA_EUNSUPPORTED;
   }
 }
@@ -442,8 +444,9 @@ struct BlockBuffers {
 // timm Block x depth: x += proj(attn(LN1 x)); x += fc2(gelu(fc1(LN2 x)))
 static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int heads, int cells, int tokens,
                       const float* wf32, const bf16* wsplit, long long split_plane, const BlockBuffers& b,
-                      int precision, cudaStream_t st) {
+                      int precision, int wls, cudaStream_t st) {
   const int M = cells * tokens;
+  const int fmt = fmt_of(precision);
   const long long pa = (long long)M * D, ph = (long long)M * 4 * D;
   const int hd = D / heads, hdp = (hd + 15) / 16 * 16;
   const int Wq = 3 * heads * hdp;                       // head-padded qkv width
@@ -451,25 +454,25 @@ static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int head
   RIBCA_REQUIRE(tensor_attention || hdp == hd, "short-sequence attention needs head_dim %% 16 == 0");
   for (int l = 0; l < depth; ++l) {
     const ribca_block_desc& w = blocks[l];
-    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln1_g, wf32 + w.ln1_b, 1e-6f, b.a, pa, st));
+    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln1_g, wf32 + w.ln1_b, 1e-6f, b.a, pa, fmt, st));
     if (tensor_attention) {
       bf16* qs = reinterpret_cast<bf16*>(b.qkv);
       const long long pq = (long long)M * Wq;
       RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
-                            RIBCA_EPI_STORE_SPLIT, nullptr, qs, pq, precision, st));
-      RIBCA_TRY(attention_tc_launch(qs, pq, cells, tokens, heads, hd, b.a, pa, st));
+                            RIBCA_EPI_STORE_SPLIT, nullptr, qs, pq, precision, wls, st));
+      RIBCA_TRY(attention_tc_launch(qs, pq, cells, tokens, heads, hd, b.a, pa, fmt, st));
     } else {
       RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
-                            RIBCA_EPI_STORE, b.qkv, nullptr, 0, precision, st));
-      RIBCA_TRY(attention_launch(b.qkv, cells, tokens, heads, hd, b.a, pa, st));
+                            RIBCA_EPI_STORE, b.qkv, nullptr, 0, precision, wls, st));
+      RIBCA_TRY(attention_launch(b.qkv, cells, tokens, heads, hd, b.a, pa, fmt, st));
     }
     RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
-                          RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, st));
-    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, b.a, pa, st));
+                          RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, wls, st));
+    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, b.a, pa, fmt, st));
     RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.fc1_w, split_plane, M, 4 * D, D, wf32 + w.fc1_b, nullptr, 0,
-                          RIBCA_EPI_GELU, nullptr, b.h, ph, precision, st));
+                          RIBCA_EPI_GELU, nullptr, b.h, ph, precision, wls, st));
     RIBCA_TRY(gemm_launch(b.h, ph, wsplit + w.fc2_w, split_plane, M, D, 4 * D, wf32 + w.fc2_b, nullptr, 0,
-                          RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, st));
+                          RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, wls, st));
   }
   return RIBCA_OK;
 }
@@ -500,15 +503,17 @@ using namespace ribca;
 extern "C" {
 
 int ribca_layernorm_split(const float* x, int M, int D, const float* gamma, const float* beta, float eps,
-                          void* out_split, long long out_plane, ribca_stream_t stream) {
+                          void* out_split, long long out_plane, int format, ribca_stream_t stream) {
   RIBCA_REQUIRE(x && gamma && beta && out_split, "ribca_layernorm_split: null pointer");
-  return layernorm_launch(x, M, D, gamma, beta, eps, out_split, out_plane, as_stream(stream));
+  RIBCA_REQUIRE(format == kFmtBf16 || format == kFmtF16F8, "ribca_layernorm_split: unknown plane format %d", format);
+  return layernorm_launch(x, M, D, gamma, beta, eps, out_split, out_plane, format, as_stream(stream));
 }
 
 int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head_dim, void* out_split,
-                    long long out_plane, ribca_stream_t stream) {
+                    long long out_plane, int format, ribca_stream_t stream) {
   RIBCA_REQUIRE(qkv && out_split && heads > 0, "ribca_attention: bad arguments");
-  return attention_launch(qkv, cells, tokens, heads, head_dim, out_split, out_plane, as_stream(stream));
+  RIBCA_REQUIRE(format == kFmtBf16 || format == kFmtF16F8, "ribca_attention: unknown plane format %d", format);
+  return attention_launch(qkv, cells, tokens, heads, head_dim, out_split, out_plane, format, as_stream(stream));
 }
 
 size_t ribca_vit_workspace_bytes(const ribca_vit_desc* desc, int n_cells) {
@@ -542,11 +547,14 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
   // patch embedding: im2col into the (larger) MLP buffer, GEMM with the cls/pos/bias row table
   const int Kpe = 16 * C;
   const long long pe_plane = M * Kpe;
-  im2col_split_kernel<<<grid_for((long long)n_cells * C * 400, 256), 256, 0, st>>>(patches, n_cells, C, b.h, b.h + pe_plane);
+  const int fmt = fmt_of(precision), wls = desc->w_log2_scale;
+  RIBCA_REQUIRE(desc->plane_format == fmt, "ribca_vit_forward: weights are packed in plane format %d but precision %d needs %d",
+                desc->plane_format, precision, fmt);
+  im2col_split_kernel<<<grid_for((long long)n_cells * C * 400, 256), 256, 0, st>>>(patches, n_cells, C, fmt, b.h, b.h + pe_plane);
   RIBCA_LAUNCH_CHECK("im2col_split_kernel");
   RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
-                        wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, st));
-  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, st));
+                        wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, wls, st));
+  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st));
   head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(b.x, n_cells, T, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
                                                          wf32 + desc->head_w, wf32 + desc->head_b, desc->classes, probs, logits);
   RIBCA_LAUNCH_CHECK("head_softmax_kernel");
@@ -603,25 +611,28 @@ int ribca_mae_impute(const ribca_mae_desc* desc, const float* wf32, const void* 
 
   // encoder (markerImputer.py:186-206)
   const long long tile_plane = Me * 1600;
-  mae_tiles_split_kernel<<<grid_for(Me * 400, 256), 256, 0, st>>>(patches, n_cells, L, pl, be.h, be.h + tile_plane);
+  const int fmt = fmt_of(precision), wls = desc->w_log2_scale;
+  RIBCA_REQUIRE(desc->plane_format == fmt, "ribca_mae_impute: weights are packed in plane format %d but precision %d needs %d",
+                desc->plane_format, precision, fmt);
+  mae_tiles_split_kernel<<<grid_for(Me * 400, 256), 256, 0, st>>>(patches, n_cells, L, pl, fmt, be.h, be.h + tile_plane);
   RIBCA_LAUNCH_CHECK("mae_tiles_split_kernel");
   mae_enc_table_kernel<<<grid_for((long long)Te * De, 256), 256, 0, st>>>(wf32 + desc->cls_token, wf32 + desc->embed_bias,
                                                                          wf32 + desc->pos_embed, De, pl, table);
   RIBCA_LAUNCH_CHECK("mae_enc_table_kernel");
   RIBCA_TRY(gemm_launch(be.h, tile_plane, wsplit + desc->embed_w, desc->split_plane, (int)Me, De, 1600, nullptr, table, Te,
-                        RIBCA_EPI_STORE, be.x, nullptr, 0, precision, st));
-  RIBCA_TRY(run_blocks(desc->enc_blocks, desc->enc_depth, De, desc->enc_heads, n_cells, Te, wf32, wsplit, desc->split_plane, be, precision, st));
-  RIBCA_TRY(layernorm_launch(be.x, (int)Me, De, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f, be.a, Me * De, st));
+                        RIBCA_EPI_STORE, be.x, nullptr, 0, precision, wls, st));
+  RIBCA_TRY(run_blocks(desc->enc_blocks, desc->enc_depth, De, desc->enc_heads, n_cells, Te, wf32, wsplit, desc->split_plane, be, precision, wls, st));
+  RIBCA_TRY(layernorm_launch(be.x, (int)Me, De, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f, be.a, Me * De, fmt, st));
   // decoder (markerImputer.py:208-232)
   RIBCA_TRY(gemm_launch(be.a, Me * De, wsplit + desc->dec_embed_w, desc->split_plane, (int)Me, Dd, De, wf32 + desc->dec_embed_b,
-                        nullptr, 0, RIBCA_EPI_STORE, emb, nullptr, 0, precision, st));
+                        nullptr, 0, RIBCA_EPI_STORE, emb, nullptr, 0, precision, wls, st));
   mae_decoder_input_kernel<<<grid_for(Md * Dd, 256), 256, 0, st>>>(emb, wf32 + desc->mask_token, wf32 + desc->dec_pos_embed,
                                                                     n_cells, L, Dd, pl, bd.x);
   RIBCA_LAUNCH_CHECK("mae_decoder_input_kernel");
-  RIBCA_TRY(run_blocks(desc->dec_blocks, desc->dec_depth, Dd, desc->dec_heads, n_cells, Td, wf32, wsplit, desc->split_plane, bd, precision, st));
-  RIBCA_TRY(layernorm_launch(bd.x, (int)Md, Dd, wf32 + desc->dec_norm_g, wf32 + desc->dec_norm_b, 1e-6f, bd.a, Md * Dd, st));
+  RIBCA_TRY(run_blocks(desc->dec_blocks, desc->dec_depth, Dd, desc->dec_heads, n_cells, Td, wf32, wsplit, desc->split_plane, bd, precision, wls, st));
+  RIBCA_TRY(layernorm_launch(bd.x, (int)Md, Dd, wf32 + desc->dec_norm_g, wf32 + desc->dec_norm_b, 1e-6f, bd.a, Md * Dd, fmt, st));
   RIBCA_TRY(gemm_launch(bd.a, Md * Dd, wsplit + desc->pred_w, desc->split_plane, (int)Md, 1600, Dd, wf32 + desc->pred_b, nullptr, 0,
-                        RIBCA_EPI_STORE, pred, nullptr, 0, precision, st));
+                        RIBCA_EPI_STORE, pred, nullptr, 0, precision, wls, st));
   mae_scatter_kernel<<<grid_for((long long)n_cells * L * 400, 256), 256, 0, st>>>(pred, n_cells, L, pl, patches);
   RIBCA_LAUNCH_CHECK("mae_scatter_kernel");
   return RIBCA_OK;

@@ -1,7 +1,8 @@
 """Device-resident classifier / imputer engines over ribca_vit_forward and ribca_mae_impute.
 
 A timm-format state dict (reference checkpoint layout, model.py:191, markerImputer.py:261,285) is
-packed once into two device blobs - fp32 parameters and split-bf16 GEMM weights {hi, lo} - plus a
+packed once into two device blobs - fp32 parameters and the GEMM weights as two 16-bit operand planes
+(bf16 {hi, lo}, or fp16 + e4m3 pairs for the default "f16f8" precision; csrc/common.cuh) - plus a
 C descriptor of element offsets (include/ribca_b200.h: ribca_vit_desc / ribca_mae_desc).
 """
 from __future__ import annotations
@@ -40,11 +41,14 @@ class _Packer:
         self.mat_off += p.numel()
         return off
 
-    def finish(self, device):
+    def finish(self, device, fmt: int = ops.FMT_BF16):
+        """-> (fp32 blob, (2, total) 16-bit weight planes, plane stride, w_log2_scale)."""
         wf32 = torch.cat(self.f32).to(device)
         mats = torch.cat(self.mat).to(device)
-        wsplit = ops.split_bf16(mats)                 # (2, total) bf16, plane stride = total
-        return wf32, wsplit, self.mat_off
+        if fmt == ops.FMT_BF16:
+            return wf32, ops.split_bf16(mats), self.mat_off, 0
+        t = ops.weight_log2_scale(float(mats.abs().max().item()))
+        return wf32, ops.split_planes(mats, fmt, w_role=True, log2_scale=t), self.mat_off, t + 8
 
 
 def _pad_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
@@ -88,7 +92,7 @@ _WS = _Workspace()
 class VitEngine:
     """One panel's ViT classifier (reference model.py:31-88) resident on a CUDA device."""
 
-    def __init__(self, spec: VitSpec | str, state_dict: dict, device="cuda", precision: str = "bf16x3",
+    def __init__(self, spec: VitSpec | str, state_dict: dict, device="cuda", precision: str = ops.DEFAULT_PRECISION,
                  max_cells_per_call: int = 4096):
         self.spec = VIT_SPECS[spec] if isinstance(spec, str) else spec
         self.device = torch.device(device)
@@ -113,7 +117,8 @@ class VitEngine:
         d.head_w = pk.add_f32(sd["head.weight"]); d.head_b = pk.add_f32(sd["head.bias"])
         for i in range(s.depth):
             _pack_block(pk, sd, f"blocks.{i}", d.blocks[i], s.heads)
-        self.wf32, self.wsplit, d.split_plane = pk.finish(self.device)
+        d.plane_format = ops.plane_format(precision)
+        self.wf32, self.wsplit, d.split_plane, d.w_log2_scale = pk.finish(self.device, d.plane_format)
         self.desc = d
 
     def set_head(self, weight: torch.Tensor, bias: torch.Tensor):
@@ -148,7 +153,7 @@ class VitEngine:
 class MaeEngine:
     """One panel's MAE marker imputer (reference markerImputer.py:69-329) resident on a CUDA device."""
 
-    def __init__(self, spec: MaeSpec | str, state_dict: dict, device="cuda", precision: str = "bf16x3",
+    def __init__(self, spec: MaeSpec | str, state_dict: dict, device="cuda", precision: str = ops.DEFAULT_PRECISION,
                  max_cells_per_call: int = 8192):
         self.spec = MAE_SPECS[spec] if isinstance(spec, str) else spec
         self.device = torch.device(device)
@@ -175,7 +180,8 @@ class MaeEngine:
             _pack_block(pk, sd, f"blocks.{i}", d.enc_blocks[i], s.enc_heads)
         for i in range(s.dec_depth):
             _pack_block(pk, sd, f"decoder_blocks.{i}", d.dec_blocks[i], s.dec_heads)
-        self.wf32, self.wsplit, d.split_plane = pk.finish(self.device)
+        d.plane_format = ops.plane_format(precision)
+        self.wf32, self.wsplit, d.split_plane, d.w_log2_scale = pk.finish(self.device, d.plane_format)
         self.desc = d
 
     @torch.no_grad()

@@ -17,7 +17,22 @@ from . import _lib
 PATCH = 40
 MAX_PANEL_CH = 16
 GAUSS_STRIDE = 16
-PRECISION = {"bf16x3": 0, "bf16": 1, "bf16x1": 1, "simt": 2, "fp32": 2}
+PRECISION = {"bf16x3": 0, "bf16": 1, "bf16x1": 1, "simt": 2, "fp32": 2, "f16f8": 3}
+DEFAULT_PRECISION = "f16f8"
+FMT_BF16, FMT_F16F8 = 0, 1                      # ribca_plane_format
+
+
+def plane_format(precision: str) -> int:
+    return FMT_F16F8 if PRECISION[precision] == 3 else FMT_BF16
+
+
+def weight_log2_scale(max_abs: float) -> int:
+    """t of the f16f8 weight packing: the largest power of two with max|w| * 2^t <= 128, so that the e4m3 copies
+    (|.| <= 448) and the fp16 main plane (w * 2^(t+8) <= 32768) stay finite."""
+    import math
+    if not max_abs > 0.0 or not math.isfinite(max_abs):
+        return 0
+    return int(max(-20, min(30, math.floor(math.log2(128.0 / max_abs)))))
 EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_STORE_SPLIT = 0, 1, 2, 3
 _DTYPES = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2, torch.int32: 3}
 
@@ -256,9 +271,19 @@ def split_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split_planes(x: torch.Tensor, fmt: int = FMT_F16F8, w_role: bool = False, log2_scale: int = 0) -> torch.Tensor:
+    """fp32 tensor -> (2, *shape) 16-bit operand planes in `fmt` (A role, or W role scaled by 2^log2_scale)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16 if fmt == FMT_BF16 else torch.int16, device=x.device)
+    _lib.check(_lib.lib().ribca_split_planes(_ptr(x), x.numel(), fmt, int(bool(w_role)), int(log2_scale), _ptr(out[0]),
+                                             _ptr(out[1]), _stream()), "ribca_split_planes")
+    return out
+
+
 def gemm(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None, epilogue=EPI_STORE,
-         out=None, precision="bf16x3"):
-    """out (+)= A . W^T with A (2, M, K), W (2, N, K) split-bf16; see ribca_gemm_splitbf16."""
+         out=None, precision="bf16x3", w_log2_scale: int = 0):
+    """out (+)= A . W^T with A (2, M, K), W (2, N, K) operand planes; see ribca_gemm_splitbf16."""
     _need_cuda(a_split, w_split, bias, row_table, out)
     _, m, k = a_split.shape
     _, n, k2 = w_split.shape
@@ -266,43 +291,48 @@ def gemm(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None
     dev = a_split.device
     out_f32 = out_split = None
     if epilogue in (EPI_GELU, EPI_STORE_SPLIT):
-        out_split = out if out is not None else torch.empty((2, m, n), dtype=torch.bfloat16, device=dev)
+        f8 = plane_format(precision) == FMT_F16F8 and epilogue == EPI_GELU
+        out_split = out if out is not None else torch.empty((2, m, n), dtype=torch.int16 if f8 else torch.bfloat16, device=dev)
     else:
         out_f32 = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=dev)
     period = row_table.shape[0] if row_table is not None else 0
     _lib.check(_lib.lib().ribca_gemm_splitbf16(_ptr(a_split), m * k, _ptr(w_split), n * k, m, n, k, _ptr(bias), _ptr(row_table),
                                                period, epilogue, _ptr(out_f32), _ptr(out_split), m * n, PRECISION[precision],
-                                               _stream()), "ribca_gemm_splitbf16")
+                                               int(w_log2_scale), _stream()), "ribca_gemm_splitbf16")
     return out_split if epilogue in (EPI_GELU, EPI_STORE_SPLIT) else out_f32
 
 
-def layernorm_split(x: torch.Tensor, gamma, beta, eps=1e-6) -> torch.Tensor:
+def _planes(shape, fmt, device):
+    return torch.empty((2,) + tuple(shape), dtype=torch.bfloat16 if fmt == FMT_BF16 else torch.int16, device=device)
+
+
+def layernorm_split(x: torch.Tensor, gamma, beta, eps=1e-6, fmt: int = FMT_BF16) -> torch.Tensor:
     _need_cuda(x, gamma, beta)
     m, d = x.shape
-    out = torch.empty((2, m, d), dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.lib().ribca_layernorm_split(_ptr(x), m, d, _ptr(gamma), _ptr(beta), eps, _ptr(out), m * d, _stream()),
+    out = _planes((m, d), fmt, x.device)
+    _lib.check(_lib.lib().ribca_layernorm_split(_ptr(x), m, d, _ptr(gamma), _ptr(beta), eps, _ptr(out), m * d, fmt, _stream()),
                "ribca_layernorm_split")
     return out
 
 
-def attention(qkv: torch.Tensor, cells: int, tokens: int, heads: int) -> torch.Tensor:
+def attention(qkv: torch.Tensor, cells: int, tokens: int, heads: int, fmt: int = FMT_BF16) -> torch.Tensor:
     _need_cuda(qkv)
     m, d3 = qkv.shape
     d = d3 // 3
-    out = torch.empty((2, m, d), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.lib().ribca_attention(_ptr(qkv), cells, tokens, heads, d // heads, _ptr(out), m * d, _stream()),
+    out = _planes((m, d), fmt, qkv.device)
+    _lib.check(_lib.lib().ribca_attention(_ptr(qkv), cells, tokens, heads, d // heads, _ptr(out), m * d, fmt, _stream()),
                "ribca_attention")
     return out
 
 
-def attention_tc(qkv_split: torch.Tensor, cells: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
-    """Tensor-core attention: qkv_split (2, M, 3*heads*hdp) bf16 planes -> (2, M, heads*head_dim)."""
+def attention_tc(qkv_split: torch.Tensor, cells: int, tokens: int, heads: int, head_dim: int, fmt: int = FMT_BF16) -> torch.Tensor:
+    """Tensor-core attention: qkv_split (2, M, 3*heads*hdp) bf16 planes -> (2, M, heads*head_dim) planes in `fmt`."""
     _need_cuda(qkv_split)
     _, m, wq = qkv_split.shape
     d = heads * head_dim
-    out = torch.empty((2, m, d), dtype=torch.bfloat16, device=qkv_split.device)
+    out = _planes((m, d), fmt, qkv_split.device)
     _lib.check(_lib.lib().ribca_attention_tc(_ptr(qkv_split), m * wq, cells, tokens, heads, head_dim, _ptr(out), m * d,
-                                             _stream()), "ribca_attention_tc")
+                                             fmt, _stream()), "ribca_attention_tc")
     return out
 
 

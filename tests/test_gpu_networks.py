@@ -1,4 +1,4 @@
-"""GPU parity tests for stage 4 (tcgen05 split-bf16 GEMM, LayerNorm, attention, ViT, MAE) and the
+"""GPU parity tests for stage 4 (tcgen05 GEMM in both operand formats, LayerNorm, attention, ViT, MAE) and the
 end-to-end Annotator, against torch fp32/fp64 references of the same op, the CPU oracle, and the
 reference-generated golden fixtures.
 
@@ -25,12 +25,21 @@ def _unsplit(t):
     return t[0].double() + t[1].double()
 
 
+def _unsplit_f16f8(t):
+    """Value an f16f8 A-role operand stands for: fp16 plane + e4m3(low byte of the pair plane) / 2^8."""
+    hi = t[0].view(torch.float16).double()
+    lo = (t[1].view(torch.uint8).reshape(t[1].shape + (2,))[..., 0].contiguous().view(torch.float8_e4m3fn)).double()
+    return hi + lo / 256.0
+
+
 def _gemm_case(m, n, k, precision, epilogue=ops.EPI_STORE, bias=True, table_period=0, seed=0):
     g = torch.Generator(device=DEV).manual_seed(seed)
     a = torch.randn((m, k), generator=g, device=DEV)
     w = torch.randn((n, k), generator=g, device=DEV) * 0.05
     b = torch.randn(n, generator=g, device=DEV) if bias else None
     tab = torch.randn((table_period, n), generator=g, device=DEV) if table_period else None
+    if precision == "f16f8":
+        return _gemm_case_f16f8(a, w, b, tab, epilogue, g)
     a_s, w_s = ops.split_bf16(a), ops.split_bf16(w)
     ref = _unsplit(a_s) @ _unsplit(w_s).T
     bound = (_unsplit(a_s).abs() @ _unsplit(w_s).abs().T)
@@ -55,6 +64,36 @@ def _gemm_case(m, n, k, precision, epilogue=ops.EPI_STORE, bias=True, table_peri
     return err.max().item(), rel, ref.abs().max().item()
 
 
+def _gemm_case_f16f8(a, w, b, tab, epilogue, g):
+    """fp16 main pass + e4m3 correction pass against the exact fp64 product of the fp32 operands."""
+    m, n = a.shape[0], w.shape[0]
+    t = ops.weight_log2_scale(float(w.abs().max().item()))
+    a_s = ops.split_planes(a, ops.FMT_F16F8)
+    w_s = ops.split_planes(w, ops.FMT_F16F8, w_role=True, log2_scale=t)
+    ref = a.double() @ w.double().T
+    bound = a.double().abs() @ w.double().abs().T
+    if b is not None:
+        ref = ref + b.double()
+    if tab is not None:
+        ref = ref + tab.double()[torch.arange(m, device=DEV) % tab.shape[0]]
+    kw = dict(precision="f16f8", w_log2_scale=t + 8)
+    if epilogue == ops.EPI_RESIDUAL:
+        out0 = torch.randn((m, n), generator=g, device=DEV)
+        ref = ref + out0.double()
+        got = ops.gemm(a_s, w_s, b, tab, epilogue, out=out0.clone(), **kw).double()
+    elif epilogue == ops.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+        got = _unsplit_f16f8(ops.gemm(a_s, w_s, b, tab, epilogue, **kw))
+    elif epilogue == ops.EPI_STORE_SPLIT:
+        got = _unsplit(ops.gemm(a_s, w_s, b, tab, epilogue, **kw))
+    else:
+        got = ops.gemm(a_s, w_s, b, tab, epilogue, **kw).double()
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    rel = (err / bound.clamp_min(1e-6)).max().item()
+    return err.max().item(), rel, ref.abs().max().item()
+
+
 GEMM_SHAPES = [(128, 192, 64), (128, 16, 48), (256, 576, 576), (101 * 5, 1728, 576), (1000, 288, 144), (303, 1600, 512),
                (77, 2304, 576), (4096, 576, 2304), (640, 768, 1600), (129, 144, 112)]
 
@@ -71,6 +110,48 @@ def test_gemm_tcgen05_bf16x3(m, n, k):
     err, rel, mag = _gemm_case(m, n, k, "bf16x3")
     print(f"bf16x3 M={m} N={n} K={k}: max|err|={err:.3e} rel-to-bound={rel:.3e} |ref|max={mag:.2f}")
     assert rel < 2e-5
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_tcgen05_f16f8(m, n, k):
+    """Default precision: the two correction terms are rounded to e4m3 (2^-4 of a 2^-11 term each), so the error
+    is bounded by 2^-14 * sum |a||w| in the worst case and is ~1e-5 of it for random operands."""
+    err, rel, mag = _gemm_case(m, n, k, "f16f8")
+    print(f"f16f8 M={m} N={n} K={k}: max|err|={err:.3e} rel-to-bound={rel:.3e} |ref|max={mag:.2f}")
+    assert rel < 2.0 ** -14
+
+
+@pytest.mark.parametrize("epilogue,period", [(ops.EPI_RESIDUAL, 0), (ops.EPI_GELU, 0), (ops.EPI_STORE, 101), (ops.EPI_STORE_SPLIT, 0)])
+def test_gemm_tcgen05_f16f8_epilogues(epilogue, period):
+    err, rel, mag = _gemm_case(101 * 7, 576, 288, "f16f8", epilogue, True, period, seed=3)
+    print(f"f16f8 epilogue {epilogue} period {period}: max|err|={err:.3e} rel={rel:.3e}")
+    assert rel < 2.0 ** -13        # + the output's own quantisation (2^-15 relative for the f16f8 planes)
+
+
+def test_f16f8_activation_planes():
+    """LayerNorm / attention outputs in the f16f8 A-role format decode to the fp32 value within 2^-15 relative."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn((101 * 3, 576), generator=g, device=DEV) * 2 + 0.3
+    gam = torch.randn(576, generator=g, device=DEV)
+    bet = torch.randn(576, generator=g, device=DEV)
+    want = torch.nn.functional.layer_norm(x.double(), (576,), gam.double(), bet.double(), 1e-6)
+    got = _unsplit_f16f8(ops.layernorm_split(x, gam, bet, 1e-6, fmt=ops.FMT_F16F8))
+    # e4m3 of the scaled remainder: 2^-4 relative in its normal range, 2^-10 absolute below 2^-6 (-> 2^-18 of x)
+    assert ((got - want).abs() <= 2.0 ** -15 * want.abs() + 2.0 ** -18 + 3e-6).all()
+    v = torch.randn((4096,), generator=g, device=DEV) * 3
+    dec = _unsplit_f16f8(ops.split_planes(v, ops.FMT_F16F8))
+    assert ((dec - v.double()).abs() <= 2.0 ** -15 * v.double().abs() + 2.0 ** -18).all()
+    # the second e4m3 of each pair is the fp16 value rounded to 4 significant bits
+    pl = ops.split_planes(v, ops.FMT_F16F8)
+    hi8 = pl[1].view(torch.uint8).reshape(-1, 2)[:, 1].contiguous().view(torch.float8_e4m3fn).double()
+    assert ((hi8 - v.double()).abs() <= 2.0 ** -4 * v.double().abs() + 2.0 ** -9).all()
+    for cells, tokens, heads, hd in ((3, 101, 12, 48), (5, 7, 12, 64)):
+        d = heads * hd
+        qkv = torch.randn((cells * tokens, 3 * d), generator=g, device=DEV)
+        q, k, vv = qkv.view(cells, tokens, 3, heads, hd).permute(2, 0, 3, 1, 4).double().unbind(0)
+        want = torch.nn.functional.scaled_dot_product_attention(q, k, vv).transpose(1, 2).reshape(cells * tokens, d)
+        got = _unsplit_f16f8(ops.attention(qkv, cells, tokens, heads, fmt=ops.FMT_F16F8))
+        assert (got - want).abs().max().item() < 4e-5
 
 
 @pytest.mark.parametrize("epilogue,period", [(ops.EPI_RESIDUAL, 0), (ops.EPI_GELU, 0), (ops.EPI_STORE, 101)])
@@ -120,7 +201,9 @@ def test_attention_tensor_core_vs_torch(cells, tokens, heads, hd):
     q, k, v = exact.view(cells, tokens, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
     want = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(m, heads * hd)
     got = _unsplit(ops.attention_tc(qs, cells, tokens, heads, hd))
+    got8 = _unsplit_f16f8(ops.attention_tc(qs, cells, tokens, heads, hd, fmt=ops.FMT_F16F8))
     torch.cuda.synchronize()
+    assert (got8 - want).abs().max().item() < 2.0 ** -14 * max(1.0, want.abs().max().item())
     err = (got - want).abs().max().item()
     print(f"attention_tc cells={cells} tokens={tokens} heads={heads} hd={hd}: max|err|={err:.3e} |ref|max={want.abs().max().item():.2f}")
     # the output itself is quantised to split-bf16 (16 mantissa bits): 2^-16 of its magnitude
@@ -138,18 +221,29 @@ def _vit_pair(panel, seed=1):
 def test_vit_reference_golden(golden_dir, panel):
     g = np.load(os.path.join(golden_dir, "vit.npz"))
     sd, _ = _vit_pair(panel)
-    eng = engine.VitEngine(panel, sd, DEV)
+    engines = {"f16f8": engine.VitEngine(panel, sd, DEV), "bf16x3": engine.VitEngine(panel, sd, DEV, precision="bf16x3")}
+    engines["simt"] = engines["bf16x3"]                 # same bf16 {hi, lo} planes on the FP32 pipe
+    assert engines["f16f8"].precision == "f16f8"        # the default
     x = torch.from_numpy(g[panel + "_x"]).to(DEV)
-    for prec, tol_logit, tol_prob in (("bf16x3", 2e-4, 1e-4), ("simt", 5e-5, 2e-5)):
-        probs, logits = eng.forward(x, return_logits=True, precision=prec)
+    for prec, tol_logit, tol_prob in (("f16f8", 6e-4, 3e-4), ("bf16x3", 2e-4, 1e-4), ("simt", 5e-5, 2e-5)):
+        probs, logits = engines[prec].forward(x, return_logits=True, precision=prec)
         dl = np.abs(logits.cpu().numpy() - g[panel + "_logits"]).max()
         dp = np.abs(probs.cpu().numpy() - g[panel + "_probs"]).max()
         print(f"{panel} {prec}: max|dlogit|={dl:.3e} max|dprob|={dp:.3e}")
         assert dl < tol_logit and dp < tol_prob
 
 
+def test_precision_must_match_packed_weights():
+    sd, _ = _vit_pair("nerve_cell")
+    eng = engine.VitEngine("nerve_cell", sd, DEV)           # f16f8 planes
+    x = torch.zeros((2, 3, 40, 40), device=DEV)
+    with pytest.raises(RuntimeError, match="plane format"):
+        eng.forward(x, precision="bf16x3")
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 @pytest.mark.parametrize("panel", ["immune_base", "immune_extended", "immune_full", "structure", "nerve_cell"])
-def test_vit_vs_oracle_on_real_patches(panel):
+def test_vit_vs_oracle_on_real_patches(panel, precision):
     spec = weights.VIT_SPECS[panel]
     mask = synth.synth_mask(160, 160, seed=6)
     img = orc.normalize(synth.to_uint16(synth.synth_image(mask, spec.in_chans, seed=6)), 0.3, 99.8)
@@ -160,23 +254,24 @@ def test_vit_vs_oracle_on_real_patches(panel):
     sd = weights.calibrate_head(sd, mean_logits, 20.0)
     ref.load_state_dict(sd)
     want = orc.vit_probs(ref, patches)
-    eng = engine.VitEngine(panel, sd, DEV, max_cells_per_call=50)      # exercises chunking
+    eng = engine.VitEngine(panel, sd, DEV, max_cells_per_call=50, precision=precision)      # exercises chunking
     got = eng.forward(torch.from_numpy(patches).to(DEV)).cpu().numpy()
     dp = np.abs(got - want).max()
     flips = int((got.argmax(1) != want.argmax(1)).sum())
     gap = np.sort(want, 1)
     gap = gap[:, -1] - gap[:, -2]
-    print(f"{panel}: cells={len(want)} max|dprob|={dp:.3e} argmax flips={flips} min top-2 gap={gap.min():.3e} "
+    print(f"{panel} {precision}: cells={len(want)} max|dprob|={dp:.3e} argmax flips={flips} min top-2 gap={gap.min():.3e} "
           f"label histogram={np.bincount(want.argmax(1), minlength=want.shape[1]).tolist()}")
     assert dp < 1e-3
     assert flips <= int((gap < 2 * dp).sum())          # a flip is only possible inside the error band
 
 
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 @pytest.mark.parametrize("panel,present", [("immune_base", [0, 1, 2, 3, 4, 6]), ("immune_extended", [0, 1, 2, 4, 5, 6, 7, 9]),
                                            ("immune_full", [0, 1, 2, 3, 4, 6, 7, 8, 9, 11, 13, 14])])
-def test_mae_vs_oracle_and_golden(golden_dir, panel, present):
+def test_mae_vs_oracle_and_golden(golden_dir, panel, present, precision):
     sd = weights.random_mae_state(panel, seed=1)
-    eng = engine.MaeEngine(panel, sd, DEV)
+    eng = engine.MaeEngine(panel, sd, DEV, precision=precision)
     g = np.load(os.path.join(golden_dir, "mae.npz"))
     if panel + "_x" in g:
         x, want = g[panel + "_x"], g[panel + "_out"]
@@ -192,7 +287,7 @@ def test_mae_vs_oracle_and_golden(golden_dir, panel, present):
     for c in present:
         assert np.array_equal(got[:, c], x[:, c])
     d = np.abs(got - want).max()
-    print(f"mae {panel}: max|d|={d:.3e} range of imputed values [{want.min():.3f}, {want.max():.3f}]")
+    print(f"mae {panel} {precision}: max|d|={d:.3e} range of imputed values [{want.min():.3f}, {want.max():.3f}]")
     assert d < 1e-3
 
 
