@@ -258,6 +258,26 @@ attention_small_kernel(const float* __restrict__ qkv, int n_items, int tokens, i
   }
 }
 
+// ---- class-token rows of the last block ---------------------------------------------------------
+// The classifier reads only token 0 of the final LayerNorm (model.py:61-62), and after the last block's attention
+// every remaining op (proj, residual, LN2, fc1, GELU, fc2, residual) is row-wise: only the class-token rows are
+// computed.  This kernel compacts them: x_cls[cell] = x[cell * tokens], same for the two operand planes of O.
+__global__ void __launch_bounds__(256)
+gather_cls_rows_kernel(const float* __restrict__ x, const uint16_t* __restrict__ a, long long a_plane, int n_cells, int tokens, int D,
+                       float* __restrict__ x_cls, uint16_t* __restrict__ a_cls, long long a_cls_plane) {
+  const int per_row = D / 4;                       // float4 / uint2 units
+  const long long total = (long long)n_cells * per_row;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long cell = t / per_row;
+    const int q = (int)(t - cell * per_row);
+    const long long src = cell * tokens * D + 4 * q, dst = cell * D + 4 * q;
+    *reinterpret_cast<float4*>(x_cls + dst) = *reinterpret_cast<const float4*>(x + src);
+    *reinterpret_cast<uint2*>(a_cls + dst) = *reinterpret_cast<const uint2*>(a + src);
+    *reinterpret_cast<uint2*>(a_cls + a_cls_plane + dst) = *reinterpret_cast<const uint2*>(a + a_plane + src);
+  }
+}
+
 // ---- final LayerNorm on the class token + head + softmax --------------------------------------
 // one warp per cell (model.py:61-62 + timm forward_head + softmax(dim=1) of model.py:404)
 __global__ void __launch_bounds__(256)
@@ -442,9 +462,11 @@ struct BlockBuffers {
 };
 
 // timm Block x depth: x += proj(attn(LN1 x)); x += fc2(gelu(fc1(LN2 x)))
+// cls_rows != nullptr: the last block computes proj / MLP for the class-token rows only and leaves them,
+// compacted, in *cls_rows ([cells][D] fp32, carved from the MLP buffer)
 static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int heads, int cells, int tokens,
                       const float* wf32, const bf16* wsplit, long long split_plane, const BlockBuffers& b,
-                      int precision, int wls, cudaStream_t st) {
+                      int precision, int wls, cudaStream_t st, float** cls_rows = nullptr) {
   const int M = cells * tokens;
   const int fmt = fmt_of(precision);
   const long long pa = (long long)M * D, ph = (long long)M * 4 * D;
@@ -465,6 +487,26 @@ static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int head
       RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
                             RIBCA_EPI_STORE, b.qkv, nullptr, 0, precision, wls, st));
       RIBCA_TRY(attention_launch(b.qkv, cells, tokens, heads, hd, b.a, pa, fmt, st));
+    }
+    if (cls_rows && l == depth - 1) {
+      // compact buffers inside the (idle) MLP buffer: x_cls fp32 [cells][D], a_cls planes [2][cells][D], h_cls planes [2][cells][4D]
+      char* base = reinterpret_cast<char*>(b.h);
+      float* x_cls = reinterpret_cast<float*>(base);
+      bf16* a_cls = reinterpret_cast<bf16*>(base + align_up((size_t)cells * D * 4, 256));
+      bf16* h_cls = reinterpret_cast<bf16*>(reinterpret_cast<char*>(a_cls) + align_up((size_t)cells * D * 4, 256));
+      const long long pc = (long long)cells * D, phc = (long long)cells * 4 * D;
+      gather_cls_rows_kernel<<<grid_for((long long)cells * (D / 4), 256), 256, 0, st>>>(
+          b.x, reinterpret_cast<const uint16_t*>(b.a), pa, cells, tokens, D, x_cls, reinterpret_cast<uint16_t*>(a_cls), pc);
+      RIBCA_LAUNCH_CHECK("gather_cls_rows_kernel");
+      RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.proj_w, split_plane, cells, D, D, wf32 + w.proj_b, nullptr, 0,
+                            RIBCA_EPI_RESIDUAL, x_cls, nullptr, 0, precision, wls, st));
+      RIBCA_TRY(layernorm_launch(x_cls, cells, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, a_cls, pc, fmt, st));
+      RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.fc1_w, split_plane, cells, 4 * D, D, wf32 + w.fc1_b, nullptr, 0,
+                            RIBCA_EPI_GELU, nullptr, h_cls, phc, precision, wls, st));
+      RIBCA_TRY(gemm_launch(h_cls, phc, wsplit + w.fc2_w, split_plane, cells, D, 4 * D, wf32 + w.fc2_b, nullptr, 0,
+                            RIBCA_EPI_RESIDUAL, x_cls, nullptr, 0, precision, wls, st));
+      *cls_rows = x_cls;
+      return RIBCA_OK;
     }
     RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
                           RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, wls, st));
@@ -554,8 +596,9 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
   RIBCA_LAUNCH_CHECK("im2col_split_kernel");
   RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
                         wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, wls, st));
-  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st));
-  head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(b.x, n_cells, T, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
+  float* x_cls = nullptr;
+  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st, &x_cls));
+  head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x_cls, n_cells, 1, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
                                                          wf32 + desc->head_w, wf32 + desc->head_b, desc->classes, probs, logits);
   RIBCA_LAUNCH_CHECK("head_softmax_kernel");
   return RIBCA_OK;
