@@ -260,8 +260,17 @@ def main():
     passes = {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1)
     gemm_tf = wk[0] / (ms[0] / 1000) / 1e12 if ms[0] > 0 else 0.0
     peak_tf = pk["bf16_tflops_sustained"]
+    # DRAM / L2 traffic of the dominant kernel per launch: from the committed ncu --set full capture (profiles/), if any
+    traffic, l2_note = None, None
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "gemm_traffic_*.json")))
+    if tfiles and args.workload == "c2" and S >= 4096:
+        tj = json.load(open(tfiles[-1]))
+        traffic = tj["mean_dram_bytes_per_launch"]
+        l2_note = {"mean_l2_to_sm_bytes_per_launch": tj["mean_l2_to_sm_bytes_per_launch"], "source": os.path.basename(tfiles[-1]),
+                   "note": "f16f8 main loop is bound by L2 -> SM delivery (~6300 B/clk chip-wide): 64 algorithmic FLOP per L2 byte at 256 x 256 pair tiles"}
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": gemm_tf / peak_tf, "traffic": None, "peak_source": pk_src + ", sustained bf16",
+                "frac": gemm_tf / peak_tf, "traffic": traffic, "l2": l2_note, "peak_source": pk_src + ", sustained bf16",
                 "launches_per_step": int(ln[0]), "avg_launch_ms": ms[0] / max(ln[0], 1), "kernel_ms_per_step": ms[0],
                 "algorithmic_flop_per_step": wk[0], "tensor_passes": passes, "issued_frac": passes * gemm_tf / peak_tf,
                 "share_of_step": ms[0] / (ms_res / args.steps),

@@ -1,20 +1,21 @@
 // Stage 4 primitive: C[M,N] = A[M,K] . W[N,K]^T (+ fused epilogue) on the 5th-gen tensor cores.
 //
 // The reference runs its ViT / MAE linears as fp32 PyTorch GEMMs (cta/model.py:397-406,
-// cta/markerImputer.py:186-232).  A single bf16 pass cannot hold the 1e-3 probability tolerance
-// (SURVEY section 7), so operands are stored as two bf16 planes x = hi + lo and the product is
-// accumulated in fp32 TMEM as  lo.hi + hi.lo + hi.hi  (three tcgen05 passes over K, "bf16x3").
-// Because the split is a data layout, the kernel is a plain K-major bf16 GEMM: every K block stages
-// the four tiles {A_hi, A_lo, W_hi, W_lo} ONCE (two TMA boxes of depth 2 over the plane axis) and
-// issues the three products from them, so the operands cross L2 -> shared memory once, not three
-// times (131 FLOP per staged byte at BN = 256); bf16x1 stages and multiplies the hi planes only.
+// cta/markerImputer.py:186-232).  A single 16-bit pass cannot hold the 1e-3 probability tolerance, so every
+// operand is stored as TWO 16-bit planes (csrc/common.cuh) and the product is accumulated in fp32 TMEM:
+//   f16f8  (default)  plane 0 fp16, plane 1 e4m3 pairs:  one kind::f8f6f4 pass over the pairs (both first-order
+//                     correction terms at once, K doubled) + one kind::f16 pass: two passes' worth of tensor time
+//   bf16x3            planes {hi, lo}:  lo.hi + hi.lo + hi.hi, three kind::f16 passes
+//   bf16x1            hi plane only (throughput / debug)
+// Because the split is a data layout, the kernel is a plain K-major GEMM: every K block stages the four tiles
+// {A_0, A_1, W_0, W_1} ONCE (two TMA boxes of depth 2 over the plane axis) and issues all products from them.
 //
-// Kernel shape (sm_100a, cta_group::1):
-//   persistent grid, one CTA per SM, 192 threads = 6 warps
+// Kernel shape (sm_100a, cta_group::2):
+//   persistent grid, one CTA per SM (CTA pairs, see below), 320 threads = 10 warps
 //     warp 0     TMA producer: 3-D tensor maps (K, rows, plane), 64B swizzle, box 32 x rows x planes,
-//                4-stage shared ring, mbarrier expect_tx; out-of-range K / rows are zero-filled by
+//                6-stage shared ring, mbarrier expect_tx; out-of-range K / rows are zero-filled by
 //                the TMA unit, so K need not be a multiple of 32 nor M of 128
-//     warp 1     allocates 512 TMEM columns, one lane issues tcgen05.mma (M=128, N=BN<=256, K=16)
+//     warp 1     allocates 512 TMEM columns, one lane (of the pair's leader) issues tcgen05.mma (M=256, N=BN<=256, K=16)
 //                from shared-memory descriptors; tcgen05.commit releases ring slots / publishes
 //                the accumulator
 //     warps 2-9  epilogue (two warps per TMEM lane quadrant, alternating column chunks): tcgen05.ld ->
@@ -22,7 +23,8 @@
 //                (full cache lines, no LSU serialisation); the residual add is a TMA reduce-add
 //                (cp.reduce.async.bulk.tensor .add.f32), so x is never read into the SM.
 //                TMEM is double-buffered (2 x 256 columns): the epilogue of tile t overlaps the main
-//                loop of tile t+1
+//                loop of tile t+1.  In f16f8 mode the main loop is bound by L2 -> shared-memory delivery
+//                (~6300 B/clk chip-wide; 64 FLOP per L2 byte at 256 x 256 pair tiles), see profiles/r01h_summary.md
 //   CTAs run as PAIRS (cluster of 2, tcgen05 cta_group::2): a pair owns a 256 x BN output tile, each CTA
 //   stages its own 128 rows of A and HALF of the W tile, and the leader CTA issues M = 256 MMAs that read
 //   both CTAs' shared memory.  Per SM this halves the B traffic (L2 -> smem and smem -> tensor core): the

@@ -1,11 +1,12 @@
-// Stage 4: the ViT classifiers and the MAE marker imputer, built on the split-bf16 tcgen05 GEMM.
+// Stage 4: the ViT classifiers and the MAE marker imputer, built on the two-plane tcgen05 GEMM.
 // Replaces VisionTransformer / vit_* + softmax (reference cta/model.py:31-88, 397-406) and
 // MaskedAutoencoderViT.forward / MarkerImputer.impute (cta/markerImputer.py:155-232, 294-329).
 //
 // Activations between kernels:  residual stream x fp32 [M][D] (M = cells * tokens);
-// every GEMM A-operand is produced directly in split-bf16 planes {hi, lo} by the kernel before it
-// (im2col, LayerNorm, attention, GELU epilogue), so no separate conversion pass touches HBM.
-// Attention (3-12 % of the FLOPs at 101 tokens) runs on the FP32 pipe with K/V staged in shared memory.
+// every GEMM A-operand is produced directly as two 16-bit planes (f16f8 or bf16 {hi, lo}, csrc/common.cuh)
+// by the kernel before it (im2col, LayerNorm, attention, GELU epilogue), so no separate conversion pass
+// touches HBM.  Attention runs on the tensor cores for the classifiers (stage4_attention.cu) and on the FP32
+// pipe, with K/V staged in shared memory, for the imputer's 7-16-token sequences.
 #include "common.cuh"
 
 namespace ribca {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""One launch of each block GEMM shape per precision (for ncu captures).  usage: tools_gemm_one.py <cells> [shape ...]"""
-import sys, torch
+"""One launch of each block GEMM shape per precision (for ncu captures).  usage: [PRECS=f16f8,bf16x3] tools_gemm_one.py <cells> [shape ...]"""
+import os, sys, torch
 sys.path.insert(0, ".")
 from multiplexed_image_annotator_b200 import ops
 cells = int(sys.argv[1]); want = sys.argv[2:] or ["fc1"]
@@ -14,7 +14,7 @@ for name in want:
     b = torch.randn(N, generator=g, device=dev)
     split = epi in (ops.EPI_GELU, ops.EPI_STORE_SPLIT)
     out = torch.zeros((2, M, N), dtype=torch.int16, device=dev) if split else torch.zeros((M, N), device=dev)
-    for prec in ("bf16x3", "f16f8", "bf16x1"):
+    for prec in os.environ.get("PRECS", "bf16x3,f16f8,bf16x1").split(","):
         if prec == "f16f8":
             a, w = ops.split_planes(af, ops.FMT_F16F8), ops.split_planes(wf, ops.FMT_F16F8, True, t)
         else:

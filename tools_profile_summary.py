@@ -35,7 +35,11 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
         "lts__t_sector_hit_rate.pct", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "smsp__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]
-import glob
+WANT += ["l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sectors.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.per_cycle_active",
+         "sm__cycles_elapsed.avg.per_second", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
+import glob, json
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+gemm_rows = []
 for rep in sorted(glob.glob(f"gpurun_out/prof_*_{tag}.ncu-rep")):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -52,4 +56,24 @@ for rep in sorted(glob.glob(f"gpurun_out/prof_*_{tag}.ncu-rep")):
                     emit(f"- {w} = {r[i]} {units[i]}")
                     break
         emit()
+        if "gemm_tcgen05" in name and rep.endswith(f"prof_gemm_{tag}.ncu-rep"):
+            def val(metric):
+                for i, h in enumerate(hdr):
+                    if h.endswith(metric):
+                        return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
+                return None
+            gemm_rows.append({"dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
+                              "l2_to_sm_bytes": val("l1tex__m_xbar2l1tex_read_bytes.sum"),
+                              "duration_ms": val("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[hdr.index([h for h in hdr if h.endswith("gpu__time_duration.sum")][0])], 1.0)})
+if gemm_rows:
+    # one launch each of the qkv / proj / fc1 / fc2 GEMMs of a vit_l block at the bench's chunk size: their mean is the
+    # per-launch DRAM traffic of the step's launch mix (each occurs once per block and chunk)
+    n = len(gemm_rows)
+    traffic = {"source": f"ncu --set full, gpurun_out/prof_gemm_{tag}.ncu-rep (tools_gemm_one.py 4096 qkv proj fc1 fc2, f16f8)",
+               "launches": gemm_rows,
+               "mean_dram_bytes_per_launch": sum(g["dram_read_bytes"] + g["dram_write_bytes"] for g in gemm_rows) / n,
+               "mean_l2_to_sm_bytes_per_launch": sum(g["l2_to_sm_bytes"] for g in gemm_rows) / n}
+    json.dump(traffic, open(f"profiles/gemm_traffic_{tag}.json", "w"), indent=1)
+    emit(f"GEMM traffic per launch (mean of {n} captures): DRAM {traffic['mean_dram_bytes_per_launch'] / 1e9:.3f} GB, "
+         f"L2 -> SM {traffic['mean_l2_to_sm_bytes_per_launch'] / 1e9:.3f} GB -> profiles/gemm_traffic_{tag}.json")
 out.close()
