@@ -38,6 +38,7 @@ extern "C" {
 #define RIBCA_MAX_TAPS 128     /* largest Gaussian radius accepted by the FIR kernels   */
 #define RIBCA_MAX_PANEL_CH 16  /* largest panel (immune_full has 15 markers)            */
 #define RIBCA_MAX_PANELS 3     /* one immune panel + structure + nerve per predict()    */
+#define RIBCA_MAX_TYPES 18     /* cell types of cta/model.py:97-99                       */
 
 typedef void* ribca_stream_t;  /* cudaStream_t */
 
@@ -122,6 +123,14 @@ int ribca_compact_cells(const int32_t* bbox, const unsigned long long* sums, con
                         int max_id, int32_t* ids, int32_t* cbbox, unsigned long long* csums,
                         int32_t* ccount, int32_t* id_to_index, int32_t* n_cells, void* workspace,
                         size_t workspace_bytes, ribca_stream_t stream);
+
+/* CSR pixel lists = the reference's cell_pos_dict itself (cta/preprocess.py:159-181): for compact cell j
+ * (label ids[j], bbox cbbox[j]) the rows / cols of its pixels in raster order are written to
+ * rows[offsets[j] .. offsets[j+1]) and cols[...]; offsets = exclusive prefix sum of ccount (n_cells + 1
+ * int64, computed by the caller).  Integer, bit-exact. */
+int ribca_cell_pixels(const int32_t* mask, int H, int W, const int32_t* ids, const int32_t* cbbox,
+                      const long long* offsets, int n_cells, int32_t* rows, int32_t* cols,
+                      ribca_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 3 - per-cell patch gather with the soft cell mask.
@@ -277,6 +286,26 @@ int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_cl
  * cta/model.py:806-858): out[p*channels + c] = mask[p] > 0 ? cell_value[id_to_index[mask[p]]*channels + c] : 0. */
 int ribca_paint_cells(const int32_t* mask, long long n_pixels, const int32_t* id_to_index, int max_id,
                       const uint8_t* cell_value, int channels, uint8_t* out, ribca_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spatial statistics on the labelled cells.
+ *   ribca_knn_2d: exact k nearest neighbours (self included, as sklearn's kneighbors on the training set) of n
+ *     points in the plane.  replaces NearestNeighbors(..., algorithm='ball_tree').kneighbors
+ *     (cta/spatial_methods.py:35-37, 97-99, 153-155).  The caller bins the points into a uniform gx x gy grid of edge
+ *     `cell` anchored at (x0, y0): xy_sorted[n][2] (float64) are the points in ascending bin order (bin = by*gx+bx),
+ *     order[s] = original index of sorted point s, bin_start[gx*gy+1] the bin offsets.  out_idx[n][k] (original
+ *     indices, row = original query index) ascending by (float64 distance, index); out_d2 (optional) squared distances.
+ *   ribca_neighbor_stats: from nbr[n][k] and types[n] (0..n_types-1), ignoring the first `skip` neighbours (the
+ *     point itself):  type_matrix[a][b] += #{(j, m): type[j]=a, type[nbr[j][m]]=b}  (spatial_methods.py:36-40; caller
+ *     zeroes / accumulates over images), and compositions[n][n_levels*n_types] = per level L the type histogram of
+ *     the L nearest neighbours divided by its sum (spatial_methods.py:157-176).  Either output may be null.
+ */
+int ribca_knn_2d(const double* xy_sorted, const int* order, const int* bin_start, int n, int k,
+                 double x0, double y0, double cell, int gx, int gy, int* out_idx, double* out_d2,
+                 ribca_stream_t stream);
+int ribca_neighbor_stats(const int* nbr, const int* types, int n, int k, int skip, int n_types,
+                         unsigned long long* type_matrix, const int* h_levels, int n_levels,
+                         double* compositions, ribca_stream_t stream);
 
 #ifdef __cplusplus
 }

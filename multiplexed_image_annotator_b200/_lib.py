@@ -116,6 +116,7 @@ SIGNATURES = {
     "ribca_cell_stats": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "ribca_compact_workspace_bytes": (_SZ, [_I]),
     "ribca_compact_cells": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ribca_cell_pixels": (_I, [_P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "ribca_build_patches": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I),
                                  C.POINTER(_P), C.POINTER(_D), _P, _P, _P]),
     "ribca_build_patches_resized": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I),
@@ -130,6 +131,8 @@ SIGNATURES = {
     "ribca_vit_forward": (_I, [C.POINTER(VitDesc), _P, _P, _P, _I, _P, _P, _P, _SZ, _I, _P]),
     "ribca_mae_workspace_bytes": (_SZ, [C.POINTER(MaeDesc), _I]),
     "ribca_mae_impute": (_I, [C.POINTER(MaeDesc), _P, _P, _P, _I, C.POINTER(_I), _I, _P, _SZ, _I, _P]),
+    "ribca_knn_2d": (_I, [_P, _P, _P, _I, _I, _D, _D, _D, _I, _I, _P, _P, _P]),
+    "ribca_neighbor_stats": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_I), _I, _P, _P]),
     "ribca_paint_cells": (_I, [_P, _LL, _P, _I, _P, _I, _P, _P]),
     "ribca_merge_votes": (_I, [_P, _I, C.POINTER(_I), _P, _I, C.POINTER(_I), _I, C.POINTER(_I), C.POINTER(_F), _F,
                                _P, _P, _P, _P]),

@@ -100,6 +100,16 @@ class _AnnotationRows:
     def __iter__(self):
         return (self[j] for j in range(len(self)))
 
+    def spatial_arrays(self):
+        """(xy float64 (n, 2) = [mean column, mean row], type index (n,), ids): what spatial_methods reads from the
+        dicts, without materialising a pixel list (np.mean of a list == integer sum / count in float64)."""
+        a, i = self._a, self._i
+        pos = a.preprocessor.cell_pos_dict[i]
+        cent = pos.sums.astype(np.float64) / pos.count.astype(np.float64)[:, None]
+        lookup = {str(t): k for k, t in enumerate(a.cell_types)}
+        types = np.array([lookup[t] for t in a.annotations[i]], dtype=np.int64)
+        return np.ascontiguousarray(cent[:, ::-1]), types, [pos._mask.dtype.type(v) for v in pos.ids]
+
 
 class Annotator(object):
     """Annotator class to predict cell types and tissue structures using the provided models."""
@@ -286,15 +296,23 @@ class Annotator(object):
         self._skipped("generate_heatmap")
 
     def neighborhood_analysis(self, n_neighbors=25, integrate=True, normalize=True):
-        self._skipped("neighborhood_analysis")
+        """reference model.py:798-800: the neighbourhood matrix CSV(s), from the GPU k-NN (the heat-map PNG is not drawn)."""
+        from .spatial_methods import neighborhood_analysis
+        return neighborhood_analysis(self.annotations_all, n_neighbors=n_neighbors, cell_types=self.cell_types, integrate=integrate,
+                                     normalize=normalize, result_dir=self.result_dir, batch_id=self.batch_id,
+                                     device=self.preprocessor.device)
 
     def tissue_region_analysis(self, n, method="kmeans"):
-        self._skipped("tissue_region_analysis")
+        """reference model.py:802-804."""
+        from .spatial_methods import tissue_region_partition
+        self.n_regions = n
+        self.tissue_regions = tissue_region_partition(self.annotations_all, n, self.n_jobs, method=method,
+                                                      device=self.preprocessor.device)
 
     def colorize(self, from_script=False):
         """reference model.py:806-858: colourised label map, confidence map and (GUI runs) the uint8 label
-        map `output_img.png` the Napari widget loads; painted on the device from the per-cell results.
-        Tissue-region maps are not produced (spatial statistics are outside the hot path)."""
+        map `output_img.png` the Napari widget loads; painted on the device from the per-cell results,
+        plus the tissue-region maps when tissue_region_analysis ran (n_regions > 0)."""
         from PIL import Image
         from .utils import number_to_rgb
         pre = self.preprocessor
@@ -318,6 +336,15 @@ class Annotator(object):
                 gui_dir = "./src/multiplexed_image_annotator/cell_type_annotation/_working_dir_temp"
                 if os.path.isdir(gui_dir):
                     Image.fromarray(ops.paint_cells(m, cells, (idx + 1).contiguous()).cpu().numpy()).save(os.path.join(gui_dir, "output_img.png"))
+            if self.n_regions > 0 and hasattr(self, "tissue_regions"):
+                reg = np.array([int(self.tissue_regions[i][k]) for k in pre.cell_pos_dict[i].ids.tolist()], dtype=np.int64)
+                reg_d = torch.from_numpy(reg.astype(np.uint8)).to(dev)
+                tcol = torch.tensor(get_colors(self.n_regions + 1), dtype=torch.uint8, device=dev)[reg_d.long()]
+                Image.fromarray(ops.paint_cells(m, cells, tcol.contiguous()).cpu().numpy()).save(
+                    os.path.join(self.result_dir, f"{self.batch_id}_tissue_region_{i}.png"))
+                if not from_script and os.path.isdir("./src/multiplexed_image_annotator/cell_type_annotation/_working_dir_temp"):
+                    Image.fromarray(ops.paint_cells(m, cells, (reg_d + 1).contiguous()).cpu().numpy()).save(
+                        "./src/multiplexed_image_annotator/cell_type_annotation/_working_dir_temp/output_img_2.png")
 
     def umap_visualization(self):
         self._skipped("umap_visualization")

@@ -30,11 +30,28 @@ CHUNK_CELLS = int(os.environ.get("RIBCA_CHUNK_CELLS", 8192))
 class CellPositions(Mapping):
     """`cell_pos_dict[i]` of the reference ({id: (rows, cols)} in raster order, ids ascending,
     cta/preprocess.py:159-181) backed by the device cell table: keys, bbox, centroid and area come
-    from the table; the pixel lists of a cell are materialised from its bbox window only when asked."""
+    from the table; the pixel lists are CSR arrays built on the device by ribca_cell_pixels the first time a
+    cell's lists are asked for (one kernel + one D2H copy for the whole image), then sliced per cell."""
 
-    def __init__(self, mask_host: np.ndarray, ids: np.ndarray, bbox: np.ndarray, sums: np.ndarray, count: np.ndarray):
+    def __init__(self, mask_host: np.ndarray, ids: np.ndarray, bbox: np.ndarray, sums: np.ndarray, count: np.ndarray,
+                 csr_source=None):
         self._mask, self.ids, self.bbox, self.sums, self.count = mask_host, ids, bbox, sums, count
         self._index = None
+        self._csr_source = csr_source      # () -> (offsets, rows, cols) device tensors, or None (host window scan)
+        self._csr = None
+
+    def csr(self):
+        """(offsets int64 (n+1,), rows int32, cols int32) numpy arrays of every cell's pixel list."""
+        if self._csr is None:
+            if self._csr_source is not None:
+                self._csr = tuple(t.cpu().numpy() for t in self._csr_source())
+            else:
+                off = np.zeros(len(self.ids) + 1, dtype=np.int64)
+                np.cumsum(self.count, out=off[1:])
+                rr, cc = np.nonzero(self._mask)                                 # raster order
+                order = np.argsort(self._mask[rr, cc], kind="stable")            # group by label, raster order kept
+                self._csr = (off, rr[order].astype(np.int32), cc[order].astype(np.int32))
+        return self._csr
 
     def __len__(self):
         return len(self.ids)
@@ -56,9 +73,8 @@ class CellPositions(Mapping):
 
     def __getitem__(self, key):
         k = self._row(key)
-        r0, r1, c0, c1 = (int(v) for v in self.bbox[k])
-        rr, cc = np.nonzero(self._mask[r0:r1 + 1, c0:c1 + 1] == int(key))
-        return (rr + r0).tolist(), (cc + c0).tolist()
+        off, rows, cols = self.csr()
+        return rows[off[k]:off[k + 1]].tolist(), cols[off[k]:off[k + 1]].tolist()
 
     def centroid(self, key):
         """(mean row, mean col) = np.mean of the lists, without materialising them."""
@@ -144,12 +160,13 @@ class ImageProcessor(object):
         host = np.ascontiguousarray(mask.cpu().numpy() if isinstance(mask, torch.Tensor) else mask)
         dev = torch.from_numpy(host.astype(np.int32)).to(self.device)
         tab = ops.cell_stats(dev)
-        return self._positions(host, tab)
+        return self._positions(host, tab, dev)
 
     @staticmethod
-    def _positions(mask_host, tab):
+    def _positions(mask_host, tab, mask_dev=None):
+        src = (lambda: ops.cell_pixels(mask_dev, tab)) if mask_dev is not None else None
         return CellPositions(mask_host, tab.ids.cpu().numpy(), tab.bbox.cpu().numpy(), tab.sums.cpu().numpy(),
-                             tab.count.cpu().numpy())
+                             tab.count.cpu().numpy(), src)
 
     def _move_image_range(self, image):
         """cta/preprocess.py:153-157."""
@@ -192,7 +209,7 @@ class ImageProcessor(object):
             self.masks_dev.append(mask_dev)
             self.cells.append(tab)
             self.min_val.append(ops.channel_min(img_dev))
-            self.cell_pos_dict.append(self._positions(mask, tab))
+            self.cell_pos_dict.append(self._positions(mask, tab, mask_dev))
             self.cell_range.append(shard_range(tab.n, rank, nranks))
             panels = self.predicted_panels()
             lo, hi = self.cell_range[i]

@@ -159,11 +159,52 @@ compact_write_kernel(const int32_t* __restrict__ bbox, const unsigned long long*
   }
 }
 
+// ---- CSR pixel lists ------------------------------------------------------------------------------
+// cell_pos_dict of the reference (cta/preprocess.py:159-181, utils.py:272-290): per cell the row list and the column
+// list of its pixels in raster order.  One warp per cell walks the cell's bbox window row by row, 32 columns at a time;
+// a ballot + prefix popcount keeps the raster order.  rows / cols of cell j land at [offsets[j], offsets[j + 1]).
+__global__ void __launch_bounds__(256)
+cell_pixels_kernel(const int32_t* __restrict__ mask, int W, const int32_t* __restrict__ ids, const int32_t* __restrict__ cbbox,
+                   const long long* __restrict__ offsets, int n_cells, int32_t* __restrict__ rows, int32_t* __restrict__ cols) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_cells; j += warps) {
+    const int id = ids[j];
+    const int4 bb = reinterpret_cast<const int4*>(cbbox)[j];          // rmin, rmax, cmin, cmax
+    long long out = offsets[j];
+    for (int r = bb.x; r <= bb.y; ++r) {
+      const int32_t* row = mask + (long long)r * W;
+      for (int c0 = bb.z; c0 <= bb.w; c0 += 32) {
+        const int c = c0 + lane;
+        const bool hit = c <= bb.w && row[c] == id;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const long long o = out + __popc(m & ((1u << lane) - 1u));
+          rows[o] = r;
+          cols[o] = c;
+        }
+        out += __popc(m);
+      }
+    }
+  }
+}
+
 }  // namespace ribca
 
 using namespace ribca;
 
 extern "C" {
+
+int ribca_cell_pixels(const int32_t* mask, int H, int W, const int32_t* ids, const int32_t* cbbox, const long long* offsets,
+                      int n_cells, int32_t* rows, int32_t* cols, ribca_stream_t stream) {
+  RIBCA_REQUIRE(mask && ids && cbbox && offsets && rows && cols, "ribca_cell_pixels: null pointer");
+  RIBCA_REQUIRE(H > 0 && W > 0 && n_cells >= 0, "ribca_cell_pixels: bad shape");
+  if (n_cells == 0) return RIBCA_OK;
+  const int blocks = std::min((n_cells + 7) / 8, num_sms() * 16);
+  cell_pixels_kernel<<<blocks, 256, 0, as_stream(stream)>>>(mask, W, ids, cbbox, offsets, n_cells, rows, cols);
+  RIBCA_LAUNCH_CHECK("cell_pixels_kernel");
+  return RIBCA_OK;
+}
 
 int ribca_mask_minmax(const int32_t* mask, long long n, int32_t* out2, ribca_stream_t stream) {
   RIBCA_REQUIRE(mask && out2 && n > 0, "ribca_mask_minmax: null pointer or empty mask");

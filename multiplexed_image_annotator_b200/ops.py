@@ -179,6 +179,23 @@ def cell_stats(mask: torch.Tensor) -> CellTable:
     return CellTable(ids[:n], cbbox[:n], csums[:n], ccount[:n], id2idx, n, hi)
 
 
+def cell_pixels(mask: torch.Tensor, cells: CellTable):
+    """The pixel lists of cell_pos_dict as CSR arrays on the device: (offsets int64 (n+1,), rows int32, cols int32);
+    cell j owns [offsets[j], offsets[j+1]) in raster order (reference preprocess.py:159-181)."""
+    _need_cuda(mask)
+    h, w = mask.shape
+    dev = mask.device
+    offsets = torch.zeros(cells.n + 1, dtype=torch.int64, device=dev)
+    if cells.n:
+        torch.cumsum(cells.count, 0, out=offsets[1:])
+    total = int(offsets[-1].item())
+    rows = torch.empty(total, dtype=torch.int32, device=dev)
+    cols = torch.empty(total, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().ribca_cell_pixels(_ptr(mask), h, w, _ptr(cells.ids), _ptr(cells.bbox), _ptr(offsets), cells.n,
+                                            _ptr(rows), _ptr(cols), _stream()), "ribca_cell_pixels")
+    return offsets, rows, cols
+
+
 # ------------------------------------------------------------------------------------------------
 # stage 3
 # ------------------------------------------------------------------------------------------------
@@ -370,3 +387,52 @@ def paint_cells(mask: torch.Tensor, cells: CellTable, cell_value: torch.Tensor) 
     _lib.check(_lib.lib().ribca_paint_cells(_ptr(mask), mask.numel(), _ptr(cells.id_to_index), cells.max_id, _ptr(cell_value), ch,
                                             _ptr(out), _stream()), "ribca_paint_cells")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# spatial statistics
+# ------------------------------------------------------------------------------------------------
+def knn_2d(xy: torch.Tensor, k: int, return_distance: bool = False, points_per_bin: float = 3.0):
+    """Exact k nearest neighbours (self included) of the rows of xy (n, 2) float64 on the device:
+    sklearn NearestNeighbors(n_neighbors=k).fit(xy).kneighbors(xy) -> indices (n, k) int32 [, distances (n, k)]."""
+    _need_cuda(xy)
+    if xy.dtype != torch.float64 or xy.dim() != 2 or xy.shape[1] != 2:
+        raise TypeError("xy must be an (n, 2) float64 tensor")
+    n = xy.shape[0]
+    if k > n:
+        raise ValueError(f"Expected n_neighbors <= n_samples, but n_samples = {n}, n_neighbors = {k}")      # sklearn's error
+    xy = xy.contiguous()
+    lo, hi = xy.min(0).values, xy.max(0).values
+    x0, y0 = float(lo[0]), float(lo[1])
+    ex, ey = max(float(hi[0]) - x0, 1e-9), max(float(hi[1]) - y0, 1e-9)
+    cell = max((points_per_bin * ex * ey / n) ** 0.5, max(ex, ey) / 4096.0, 1e-9)
+    gx, gy = int(ex / cell) + 1, int(ey / cell) + 1
+    bx = ((xy[:, 0] - x0) / cell).to(torch.int64).clamp_(0, gx - 1)
+    by = ((xy[:, 1] - y0) / cell).to(torch.int64).clamp_(0, gy - 1)
+    key, order = torch.sort(by * gx + bx, stable=True)
+    bin_start = torch.searchsorted(key, torch.arange(gx * gy + 1, device=xy.device)).to(torch.int32)
+    xy_sorted = xy[order].contiguous()
+    order32 = order.to(torch.int32)
+    idx = torch.empty((n, k), dtype=torch.int32, device=xy.device)
+    d2 = torch.empty((n, k), dtype=torch.float64, device=xy.device) if return_distance else None
+    # the kernel recomputes the bin of a query as int((x - x0) * (1 / cell)); any rounding difference against the division
+    # above only moves the ring centre by one bin, which the stopping rule (distance to the visited square) tolerates
+    _lib.check(_lib.lib().ribca_knn_2d(_ptr(xy_sorted), _ptr(order32), _ptr(bin_start), n, k, x0, y0, cell, gx, gy, _ptr(idx),
+                                       _ptr(d2), _stream()), "ribca_knn_2d")
+    return (idx, d2.sqrt_()) if return_distance else idx
+
+
+def neighbor_stats(nbr: torch.Tensor, types: torch.Tensor, n_types: int, levels=None, skip: int = 1, want_matrix: bool = True):
+    """-> (type matrix (n_types, n_types) int64 or None, compositions (n, len(levels) * n_types) float64 or None)."""
+    _need_cuda(nbr, types)
+    n, k = nbr.shape
+    types = types.to(torch.int32).contiguous()
+    mat = torch.zeros((n_types, n_types), dtype=torch.int64, device=nbr.device) if want_matrix else None
+    comp, lv, nl = None, None, 0
+    if levels:
+        nl = len(levels)
+        lv = (C.c_int * nl)(*[int(v) for v in levels])
+        comp = torch.empty((n, nl * n_types), dtype=torch.float64, device=nbr.device)
+    _lib.check(_lib.lib().ribca_neighbor_stats(_ptr(nbr), _ptr(types), n, k, skip, n_types, _ptr(mat), lv, nl, _ptr(comp), _stream()),
+               "ribca_neighbor_stats")
+    return mat, comp

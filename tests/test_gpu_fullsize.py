@@ -56,6 +56,19 @@ def test_cell_stats_full_size_against_torch_reductions(scene):
     assert int(cells.count.sum()) == int((mask > 0).sum())
 
 
+def test_cell_pixels_full_size_against_a_stable_sort(scene):
+    """CSR pixel lists of the 4096^2 mask == stable sort of the foreground pixels by label (raster order inside a cell)."""
+    mask, cells = scene["mask"], scene["cells"]
+    off, rows, cols = ops.cell_pixels(mask, cells)
+    flat = mask.reshape(-1)
+    fg = torch.nonzero(flat > 0).reshape(-1)                     # raster order
+    order = torch.sort(flat[fg].long(), stable=True).indices
+    lin = fg[order]
+    assert torch.equal(rows.long(), lin // S) and torch.equal(cols.long(), lin % S)
+    assert torch.equal(off[1:] - off[:-1], cells.count.long()) and int(off[-1]) == len(fg)
+    assert torch.equal(mask[rows.long(), cols.long()].long(), torch.repeat_interleave(cells.ids.long(), cells.count.long()))
+
+
 def test_normalize_full_size(scene):
     norm = scene["norm"]
     assert norm.shape == (15, S, S) and float(norm.min()) >= -1.0 and float(norm.max()) <= 1.0

@@ -356,5 +356,19 @@ def test_annotator_end_to_end_golden(golden_dir, tag, strict, tmp_path, monkeypa
         t = int(np.where(ann.cell_types == ann.annotations[0][j])[0][0])
         assert (rgb[rows, cols] == np.array(ann.colors[t], dtype=np.uint8)).all()
         assert (rows, cols) == tuple(a.tolist() for a in np.nonzero(mask == key))
+    # spatial statistics: the neighbourhood matrix equals the reference's loop over annotations_all with scikit-learn
+    from sklearn.neighbors import NearestNeighbors
+    m = ann.neighborhood_analysis(integrate=True, normalize=False)
+    rows_all = list(ann.annotations_all[0])
+    xy = np.array([[np.mean(r["Column"]), np.mean(r["Row"])] for r in rows_all])
+    ty = np.array([r["Cell type"] for r in rows_all])
+    idx = NearestNeighbors(n_neighbors=25, algorithm="ball_tree").fit(xy).kneighbors(xy, return_distance=False)
+    want_m = np.zeros((len(ann.cell_types),) * 2)
+    for j in range(len(xy)):
+        for kk in idx[j][1:]:
+            want_m[ty[j], ty[kk]] += 1
+    assert np.array_equal(m, want_m) and os.path.exists("results/g_integrated_neighborhood.csv")
+    with pytest.raises(ValueError):
+        ann.tissue_region_analysis(3)            # 201 neighbours of < 201 cells: scikit-learn raises in the reference too
     ann.clear_tmp()
     assert not os.path.exists("tmp")

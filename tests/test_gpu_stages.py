@@ -44,7 +44,27 @@ def _check_stats(mask_np):
     assert np.array_equal(tab.centroids().cpu().numpy(), orc.centroids(want))       # float64, bit-exact
     idx = tab.id_to_index.cpu().numpy()
     assert np.array_equal(np.nonzero(idx >= 0)[0], want["ids"])
+    # CSR pixel lists (= cell_pos_dict): every cell's rows / cols in raster order, cells in ascending id order
+    off, rows, cols = (t.cpu().numpy() for t in ops.cell_pixels(torch.from_numpy(mask_np.astype(np.int32)).to(DEV), tab))
+    rr, cc = np.nonzero(mask_np)
+    order = np.argsort(mask_np[rr, cc], kind="stable")
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(want["count"])]))
+    assert np.array_equal(rows, rr[order]) and np.array_equal(cols, cc[order])
     return tab
+
+
+def test_cell_pixels_match_the_reference_dict(golden_dir):
+    """cell_pos_dict[i][id] == (row list, col list) of the reference's _cell_pos_dict, through the lazy mapping."""
+    from multiplexed_image_annotator_b200.cell_type_annotation.preprocess import ImageProcessor
+    mask = _npz(golden_dir, "cells_example1_crop.npz")["mask"].astype(np.int32)
+    want = orc.cell_pos_dict(mask)
+    dev = torch.from_numpy(mask).to(DEV)
+    pos = ImageProcessor._positions(mask, ops.cell_stats(dev), dev)
+    assert [int(k) for k in pos] == [int(k) for k in want]
+    for cid in want:
+        assert pos[cid] == want[cid]
+        r, c = pos.centroid(cid)
+        assert r == np.mean(want[cid][0]) and c == np.mean(want[cid][1])
 
 
 @pytest.mark.parametrize("fixture", ["cells_example2.npz", "cells_example1_crop.npz"])
@@ -237,3 +257,70 @@ def test_hot_path_degenerate_inputs():
     ref = orc.make_vit("nerve_cell")
     ref.load_state_dict(weights.random_vit_state("nerve_cell", seed=1))
     assert np.abs(res.probs["nerve_cell"].cpu().numpy() - orc.vit_probs(ref, want)).max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# spatial statistics: GPU k-NN and the two reductions against scikit-learn / the reference's loops
+# ------------------------------------------------------------------------------------------------
+def _sk_knn(xy, k):
+    from sklearn.neighbors import NearestNeighbors
+    return NearestNeighbors(n_neighbors=k, algorithm="ball_tree").fit(xy).kneighbors(xy)
+
+
+@pytest.mark.parametrize("n,k,layout", [(3000, 25, "uniform"), (5000, 201, "uniform"), (4000, 25, "clustered"), (300, 201, "uniform"),
+                                        (2000, 10, "line")])
+def test_knn_matches_sklearn_ball_tree(n, k, layout):
+    rng = np.random.default_rng(n + k)
+    if layout == "uniform":
+        xy = rng.random((n, 2)) * [4096.0, 3000.0]
+    elif layout == "clustered":            # dense blobs + empty space: many empty grid rings
+        c = rng.random((8, 2)) * 5000
+        xy = c[rng.integers(0, 8, n)] + rng.normal(0, 20.0, (n, 2))
+    else:                                  # degenerate extent in y
+        xy = np.stack([rng.random(n) * 1e4, np.full(n, 7.25) + rng.random(n) * 1e-3], 1)
+    dist, idx = _sk_knn(xy, k)
+    got_idx, got_d = ops.knn_2d(torch.from_numpy(xy).to(DEV), k, return_distance=True)
+    got_idx, got_d = got_idx.cpu().numpy(), got_d.cpu().numpy()
+    assert np.array_equal(got_idx[:, 0], np.arange(n))                        # self first (distance 0)
+    np.testing.assert_allclose(got_d, dist, rtol=1e-14, atol=0)
+    same = got_idx == idx
+    if not same.all():                     # only exact distance ties may be ordered differently
+        rows = np.nonzero(~same.all(1))[0]
+        for r in rows:
+            assert np.array_equal(np.sort(got_d[r]), np.sort(dist[r]))
+            assert set(got_idx[r][got_d[r] < got_d[r, -1]]) == set(idx[r][dist[r] < dist[r, -1]])
+
+
+def test_neighbourhood_matrix_and_compositions_match_the_reference_loops(tmp_path):
+    from multiplexed_image_annotator_b200.cell_type_annotation import spatial_methods as sm
+    rng = np.random.default_rng(5)
+    n, n_types = 2500, 7
+    xy = rng.random((n, 2)) * 2048
+    types = rng.integers(0, n_types, n)
+    # reference loops (cta/spatial_methods.py:35-45 and 150-176) on scikit-learn's neighbours
+    _, idx = _sk_knn(xy, 25)
+    want = np.zeros((n_types, n_types))
+    for j in range(n):
+        for kk in idx[j][1:]:
+            want[types[j], types[kk]] += 1
+    got = sm.neighborhood_matrix(xy, types, n_types, 25, DEV)
+    assert np.array_equal(got, want)
+    _, idx = _sk_knn(xy, 201)
+    idx = idx[:, 1:]
+    comp = np.zeros((n, 8 * n_types))
+    for j in range(n):
+        for l, m in enumerate(sm.REGION_LEVELS):
+            h = np.bincount(types[idx[j, :m]], minlength=n_types).astype(np.float64)
+            comp[j, l * n_types:(l + 1) * n_types] = h / h.sum()
+    assert np.array_equal(sm.neighbor_compositions(xy, types, DEV), comp)
+    # the CSV of neighborhood_analysis: reference text format, rows normalised
+    names = np.array([f"T{t}" for t in range(n_types)])
+    rows = [{"Column": [x], "Row": [y], "Cell type": int(t), "Cell ID": j} for j, ((x, y), t) in enumerate(zip(xy, types))]
+    m = sm.neighborhood_analysis([rows], n_neighbors=25, cell_types=names, integrate=True, normalize=True, batch_id="b",
+                                 result_dir=str(tmp_path), device=DEV)
+    np.testing.assert_array_equal(m, want / want.sum(1, keepdims=True))
+    text = open(tmp_path / "b_integrated_neighborhood.csv").read().split("\n")
+    assert text[0] == "cell_type," + "".join(f"T{t}," for t in range(n_types))
+    assert text[1] == "T0," + "".join(f"{v:.3f}," for v in m[0])
+    with pytest.raises(ValueError):
+        ops.knn_2d(torch.from_numpy(xy[:10]).to(DEV), 25)                     # sklearn: n_neighbors > n_samples
