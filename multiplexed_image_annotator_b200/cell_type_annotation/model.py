@@ -291,9 +291,32 @@ class Annotator(object):
         self.logger.log(f"{what}: reporting step outside the B200 hot path, not produced by this build.")
 
     def generate_heatmap(self, integrate=False):
+        """reference model.py:700-741: mean marker intensity per predicted cell type.  The matrices are kept in
+        `self.heatmaps` ([(cell type names, (types, markers) float64)], one per image or one integrated); the PNG is drawn
+        only when matplotlib + seaborn are importable (they are presentation, absent from the offline image)."""
         if len(self.annotations) == 0:
             raise ValueError("No annotations to generate heatmap")
-        self._skipped("generate_heatmap")
+        groups = [list(range(len(self.annotations)))] if integrate else [[i] for i in range(len(self.annotations))]
+        self.heatmaps = []
+        for g, images in enumerate(groups):
+            names = np.concatenate([np.asarray(self.annotations[i]) for i in images])
+            inten = np.concatenate([np.asarray(self.preprocessor.intensity_full[i]) for i in images], axis=0)
+            assert len(inten) == len(names)
+            celltypes = np.unique(names)
+            colormap = np.stack([np.mean(inten[names == t], axis=0) for t in celltypes]) if len(celltypes) else np.zeros((0, inten.shape[1]))
+            self.heatmaps.append((celltypes, colormap))
+            f = os.path.join(self.result_dir, f"{self.batch_id}_Integrated_heatmap.png" if integrate else f"{self.batch_id}_heatmap_{g}.png")
+            try:
+                import matplotlib.pyplot as plt
+                import seaborn as sns
+            except ImportError:
+                self.logger.log(f"generate_heatmap: matplotlib / seaborn not installed, {os.path.basename(f)} not drawn (matrix kept in .heatmaps).")
+                continue
+            plt.figure(figsize=(max(colormap.shape[1] // 4, 1), max(colormap.shape[0] // 4, 1)))
+            sns.heatmap(colormap, cmap='vlag', xticklabels=self.channel_parser.markers, yticklabels=celltypes, linewidth=.5)
+            plt.tight_layout()
+            plt.savefig(f)
+            plt.close()
 
     def neighborhood_analysis(self, n_neighbors=25, integrate=True, normalize=True):
         """reference model.py:798-800: the neighbourhood matrix CSV(s), from the GPU k-NN (the heat-map PNG is not drawn)."""

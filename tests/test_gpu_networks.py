@@ -356,6 +356,12 @@ def test_annotator_end_to_end_golden(golden_dir, tag, strict, tmp_path, monkeypa
         t = int(np.where(ann.cell_types == ann.annotations[0][j])[0][0])
         assert (rgb[rows, cols] == np.array(ann.colors[t], dtype=np.uint8)).all()
         assert (rows, cols) == tuple(a.tolist() for a in np.nonzero(mask == key))
+    # heat-map reduction (reference model.py:718-727): mean intensity of the cells of each predicted type
+    ann.generate_heatmap(integrate=False)
+    types_h, hm = ann.heatmaps[0]
+    for t, row in zip(types_h, hm):
+        sel = [k for k in range(len(ann.annotations[0])) if ann.annotations[0][k] == t]
+        np.testing.assert_allclose(row, np.mean([ann.preprocessor.intensity_full[0][k] for k in sel], axis=0), rtol=1e-13)
     # spatial statistics: the neighbourhood matrix equals the reference's loop over annotations_all with scikit-learn
     from sklearn.neighbors import NearestNeighbors
     m = ann.neighborhood_analysis(integrate=True, normalize=False)
