@@ -300,7 +300,7 @@ def main():
     cpu_baseline, agreement = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        edge = min(512, S)
+        edge = min(768, S)                       # ~1850 cells, ~15 s of host work
         img_u16 = img_host.numpy()
         rate, ores, dt = cpu_oracle_rate(img_u16, mask_host.numpy(), sd_cal, edge, threads)
         crop = hp.run(np.ascontiguousarray(img_u16[:, :edge, :edge]), np.ascontiguousarray(mask_host.numpy()[:edge, :edge]),
@@ -312,6 +312,45 @@ def main():
         cpu_baseline = {"value": rate, "unit": "cells/s", "cores": threads, "kind": "port",
                         "sample": f"{edge}x{edge} crop of the same scene, {len(ores['labels'])} cells, {dt:.1f} s, "
                                   "oracle (numpy/scipy/torch fp32) preprocess+predict"}
+
+    # ---- the reference's own GPU path for stage 4 (SURVEY 8d "second baseline"): the oracle's torch modules in eager fp32
+    #      on this GPU, bs = 128 slices as cta/model.py:397-406; also the full-population parity check of the step's labels
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "c2":
+        from oracle import ribca_oracle as orc                         # checker / baseline only
+        from multiplexed_image_annotator_b200.cell_type_annotation.model import merge_on_device
+        # strict fp32 like the reference's CPU path: cuDNN would otherwise run the patch-embedding conv in TF32, which alone
+        # costs the stock GPU path ~1.5e-3 of probability (profiles/precision_population_r01.json)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref_model = orc.make_vit(panel)
+        ref_model.load_state_dict(sd_cal)
+        ref_model = ref_model.to(dev).eval()
+        full = hp.run(img_dev, mask_d, to_host=False, keep_probs=True)
+        norm = ops.normalize(img_dev, 0.3, 99.8)
+        mn = ops.channel_min(norm)
+        ref_probs, t_ref = [], 0.0
+        with torch.no_grad():
+            for a in range(0, n_cells, 8192):
+                (pt,), _, _ = ops.build_patches(norm, mask_d, mn, full.cells, [index], a, min(8192, n_cells - a))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                outs = [torch.softmax(ref_model(pt[b:b + 128]), dim=1) for b in range(0, len(pt), 128)]
+                e1.record()
+                torch.cuda.synchronize()
+                t_ref += e0.elapsed_time(e1)
+                ref_probs.append(torch.cat(outs))
+        ref_probs = torch.cat(ref_probs)
+        lab_ref, _, _ = merge_on_device({panel: ref_probs}, 0.3, None)
+        differ = int((lab_ref != full.label).sum().item())
+        ref_gpu = {"what": "oracle vit_l (plain torch.nn, eager fp32, TF32 off for matmul and cuDNN) forward + softmax on this GPU in bs = 128 slices, "
+                           "patches resident in HBM (no per-batch H2D / D2H, which the reference also pays)",
+                   "cells": n_cells, "stage4_ms": t_ref, "stage4_cells_per_s": n_cells / (t_ref / 1000),
+                   "b200_stage4_ms": ms[0] + ms[1] + ms[5],
+                   "full_population_parity": {"cells": n_cells, "labels_differ": differ, "label_agreement": 1.0 - differ / n_cells,
+                                              "max_abs_dprob": float((ref_probs - full.probs[panel]).abs().max().item())}}
+        del ref_model, ref_probs, norm, full
 
     if rank == 0:
         hist = np.bincount(res_e2e.label.numpy(), minlength=18)
@@ -333,6 +372,7 @@ def main():
                     "d2h_bytes_per_step": int(n_cells * 5 + 18 * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline, "parity_sample": agreement,
+            "reference_gpu_path": ref_gpu,
             "label_histogram": {ALL_TYPES[k]: int(v) for k, v in enumerate(hist) if v},
         }
         print(json.dumps(out))
