@@ -378,3 +378,50 @@ def test_annotator_end_to_end_golden(golden_dir, tag, strict, tmp_path, monkeypa
         ann.tissue_region_analysis(3)            # 201 neighbours of < 201 cells: scikit-learn raises in the reference too
     ann.clear_tmp()
     assert not os.path.exists("tmp")
+
+
+def _write_scene(tmp_path, name, size, n_markers, seed):
+    mask = synth.synth_mask(size, size, grid=18, seed=seed)
+    img = synth.to_uint16(synth.synth_image(mask, n_markers, seed=seed))
+    np.save(tmp_path / f"{name}_img.npy", img)
+    np.save(tmp_path / f"{name}_mask.npy", mask.numpy())
+    return mask.numpy()
+
+
+def test_cli_run_and_gui_api_full_sequence(tmp_path, monkeypatch):
+    """main.run / main.batch_run / gui_api with the reference's fixed post-processing sequence (main.py:19-28,
+    gui_api.py:19-31): heat map, annotation CSV, tissue regions, neighbourhood matrix, colourised maps, composition."""
+    import json
+    import main as cli
+    from multiplexed_image_annotator_b200.cell_type_annotation import gui_api
+    monkeypatch.chdir(tmp_path)
+    from multiplexed_image_annotator_b200.cell_type_annotation.markerParse import MarkerParser
+    markers = list(MarkerParser(strict=True).panels["immune_full"])
+    synth.write_marker_file("markers.txt", markers)
+    masks = [_write_scene(tmp_path, f"s{k}", 420, 15, 20 + k) for k in range(2)]
+    for panel in weights.VIT_SPECS:
+        bmodel.register_state(panel, weights.random_vit_state(panel, seed=4))
+    ctc = {t: -1 for t in bmodel.ALL_TYPES}
+    inten, names = cli.run("markers.txt", "s0_img.npy", "s0_mask.npy", "cuda", "./", "one", 64, True, True, -1, 3, True, 0.3, 99.8,
+                           0.3, 30, ctc, 0)
+    n0 = len(np.unique(masks[0])) - 1
+    assert n0 > 250 and len(inten) == n0 + 1 and isinstance(names, str)
+    rows = open("results/one_annotation_0.csv").read().strip().split("\n")
+    assert rows[0] == "Cell Index,Cell Type,Confidence,Row,Column,Tissue Region" and len(rows) == n0 + 1
+    nb = open("results/one_integrated_neighborhood.csv").read().strip().split("\n")
+    assert nb[0].startswith("cell_type,") and len(nb) >= 2
+    for f in ("one_colorized_annotation_0.png", "one_confidence_0.png", "one_tissue_region_0.png"):
+        assert os.path.exists(os.path.join("results", f)), f
+    assert not os.path.exists("tmp")
+    # batch CSV through the CLI entry point, then the GUI JSON entry point (regions are computed before the export there)
+    with open("batch.csv", "w") as f:
+        f.write("image_path,mask_path\ns0_img.npy,s0_mask.npy\ns1_img.npy,s1_mask.npy\n")
+    cli.batch_run("markers.txt", "batch.csv", "cuda", "./", "two", 64, True, True, -1, 0, True, 0.3, 99.8, 0.3, 30, ctc, 0)
+    assert os.path.exists("results/two_annotation_1.csv") and not os.path.exists("results/two_tissue_region_0.png")
+    os.makedirs("work", exist_ok=True)
+    json.dump({"marker_file": "markers.txt", "image_file": "s1_img.npy", "mask_file": "s1_mask.npy", "device": "cuda", "main_dir": "./",
+               "batch_size": 64, "strict": True, "infer": True, "min_cells": -1, "n_regions": 2, "normalize": True, "blur": 0.3,
+               "upper_limit": 99.8, "confidence": 0.3, "cell_size": 30, "cell_type_confidence": ctc}, open("work/hyperparams.json", "w"))
+    inten, names = gui_api.gui_api("work")
+    rows = open("results/single_run_annotation_0.csv").read().strip().split("\n")
+    assert {r.split(",")[-1] for r in rows[1:]} <= {"Region 0", "Region 1"}
