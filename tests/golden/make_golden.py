@@ -386,7 +386,52 @@ def golden_e2e():
     np.savez_compressed(os.path.join(OUT, "e2e.npz"), **out)
 
 
+def golden_c1():
+    """BASELINE configs[0]: the reference's own example mask (examples/example_1_cell_mask.png, 1850 cells) and
+    marker list (examples/markers.txt: immune_base + immune_extended + structure apply -> vit_m + vit_s, merge branch 2),
+    device='cpu'.  examples/example_1.tif is missing from the checkout, so the image is the seeded synthetic 17 x 600 x 600
+    stack painted on that mask (synth.synth_image(mask, 17, seed=1)); only the mask and the outputs are stored."""
+    from PIL import Image
+    mask = np.array(Image.open(os.path.join(REFERENCE_ROOT, "examples/example_1_cell_mask.png"))).astype(np.int32)
+    markers = [m for m in open(os.path.join(REFERENCE_ROOT, "examples/markers.txt")).read().split("\n") if m]
+    img = synth.to_uint16(synth.synth_image(torch.from_numpy(mask), len(markers), seed=1))
+    out = {"mask": mask, "markers": np.array(markers), "image_checksum": np.array([int(img.astype(np.int64).sum())], np.int64)}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            np.save("img.npy", img); np.save("mask.npy", mask)
+            synth.write_marker_file("markers.txt", markers)
+            with open("images.csv", "w") as f:
+                f.write("image_path,mask_path\nimg.npy,mask.npy\n")
+            for panel, s in weights.VIT_SPECS.items():
+                weights.save_checkpoint(weights.random_vit_state(panel, seed=2), os.path.join(weights.MODEL_DIR, s.ckpt))
+            ann = ref.model.Annotator("markers.txt", "images.csv", "cpu", "./", "c1", True, True, -1, True, 0.3, 99.8, 0.3, 30, None, n_jobs=0)
+            ann.preprocess()
+            ann.load_models()
+            for panel, attr in (("immune_extended", "immune_extended_model"), ("structure", "struct_model")):
+                x = torch.load(os.path.join("tmp", f"c1_0_{panel}_batch_0.pt"))
+                model = getattr(ann, attr)
+                with torch.no_grad():
+                    ml = model(x[:256]).mean(0).numpy()
+                out[f"meanlogits_{panel}"] = ml
+                model.load_state_dict(weights.calibrate_head(weights.random_vit_state(panel, seed=2), ml, 20.0))
+            ann.predict(128)
+            ann.export_annotations()
+            out["labels"] = np.array(ann.annotations[0])
+            out["conf"] = np.array([float(c) for c in ann.confidence[0]], np.float64)
+            out["cell_types"] = np.array([str(c) for c in ann.cell_types])
+            out["csv"] = np.array(open("results/c1_annotation_0.csv").read())
+            for panel, attr in (("immune_extended", "immune_extended_pred"), ("structure", "struct_pred")):
+                out[f"probs_{panel}"] = np.array([[d[k] for k in weights.VIT_SPECS[panel].classes] for d in getattr(ann, attr)[0]], np.float32)
+            ann.logger.close()
+        finally:
+            os.chdir(cwd)
+    print("c1 cells", len(out["labels"]), dict(zip(*np.unique(out["labels"], return_counts=True))))
+    np.savez_compressed(os.path.join(OUT, "c1.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cells", "markers", "normalize", "patches", "cellsize", "vit", "mae", "merge", "e2e"]
+    which = sys.argv[1:] or ["cells", "markers", "normalize", "patches", "cellsize", "vit", "mae", "merge", "e2e", "c1"]
     for name in which:
         globals()["golden_" + name]()

@@ -425,3 +425,50 @@ def test_cli_run_and_gui_api_full_sequence(tmp_path, monkeypatch):
     inten, names = gui_api.gui_api("work")
     rows = open("results/single_run_annotation_0.csv").read().strip().split("\n")
     assert {r.split(",")[-1] for r in rows[1:]} <= {"Region 0", "Region 1"}
+
+
+def test_c1_reference_example_configuration(golden_dir, tmp_path, monkeypatch):
+    """BASELINE configs[0] on the GPU path: example mask (1850 cells) + examples/markers.txt -> vit_m + vit_s, merge branch 2,
+    against the unmodified reference's CPU run (fixture c1.npz): labels, confidences, CSV rows, probabilities."""
+    g = np.load(os.path.join(golden_dir, "c1.npz"))
+    mask = g["mask"]
+    markers = [str(m) for m in g["markers"]]
+    img = synth.to_uint16(synth.synth_image(torch.from_numpy(mask), len(markers), seed=1))
+    assert int(img.astype(np.int64).sum()) == int(g["image_checksum"][0])
+    monkeypatch.chdir(tmp_path)
+    np.save("img.npy", img); np.save("mask.npy", mask)
+    synth.write_marker_file("markers.txt", markers)
+    with open("images.csv", "w") as f:
+        f.write("image_path,mask_path\nimg.npy,mask.npy\n")
+    for panel in weights.VIT_SPECS:
+        sd = weights.random_vit_state(panel, seed=2)
+        if f"meanlogits_{panel}" in g:
+            sd = weights.calibrate_head(sd, g[f"meanlogits_{panel}"], 20.0)
+        bmodel.register_state(panel, sd)
+    ann = bmodel.Annotator("markers.txt", "images.csv", "cuda", "./", "c1", True, True, -1, True, 0.3, 99.8, 0.3, 30, None, n_jobs=0)
+    assert ann.preprocessor.predicted_panels() == ["immune_extended", "structure"]
+    ann.preprocess()
+    ann.predict(128)
+    ann.export_annotations()
+    worst = max(float(np.abs(ann.probs[0][p] - g[f"probs_{p}"]).max()) for p in ("immune_extended", "structure"))
+    differ = [j for j, (a, b) in enumerate(zip(ann.annotations[0], g["labels"].tolist())) if a != b]
+    print(f"C1: 1850 cells, max|dprob|={worst:.3e}, labels differing={len(differ)}")
+    assert worst < 1e-3
+    # a label may only differ where the reference's own decision sits inside the probability error band
+    for j in differ:
+        votes = np.concatenate([g["probs_immune_extended"][j][:-1], g["probs_structure"][j][:-1]])        # "Others" never votes
+        top = np.sort(votes)[::-1]
+        assert min(top[0] - top[1], abs(top[0] - 0.3)) < 2 * worst, (j, ann.annotations[0][j], g["labels"][j])
+    assert len(differ) <= 2
+    conf = np.array([float(c) for c in ann.confidence[0]])
+    keep = np.ones(len(conf), bool); keep[differ] = False
+    assert np.abs(conf - g["conf"])[keep].max() < 1e-3
+    assert [str(c) for c in ann.cell_types] == g["cell_types"].tolist()
+    got_rows = open("results/c1_annotation_0.csv").read().strip().split("\n")
+    want_rows = str(g["csv"]).strip().split("\n")
+    assert len(got_rows) == len(want_rows) == 1851
+    for j, (a, b) in enumerate(zip(got_rows[1:], want_rows[1:])):
+        fa, fb = a.split(","), b.split(",")
+        assert fa[0] == fb[0] and fa[3:] == fb[3:], (a, b)            # id, centroid, region identical
+        if j not in differ:
+            assert fa[1] == fb[1] and abs(float(fa[2]) - float(fb[2])) <= 1.001e-3

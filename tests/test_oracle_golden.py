@@ -156,3 +156,35 @@ def test_end_to_end_labels(golden_dir, tag, strict, tmp_path):
     assert res["labels"] == g[tag + "_labels"].tolist()
     np.testing.assert_allclose(np.array([float(c) for c in res["confidence"]]), g[tag + "_conf"], rtol=0, atol=2e-6)
     assert np.array_equal(res["intensity"], g[tag + "_intensity"])
+
+
+def test_c1_reference_example_configuration(golden_dir, tmp_path):
+    """BASELINE configs[0]: the reference's example mask (1850 cells) + examples/markers.txt (vit_m + vit_s, merge branch 2) on
+    the seeded synthetic 17-marker image; the oracle against the unmodified reference's CPU run (fixture c1.npz)."""
+    import torch
+    from multiplexed_image_annotator_b200 import synth
+    g = _npz(golden_dir, "c1.npz")
+    mask = g["mask"]
+    markers = [str(m) for m in g["markers"]]
+    img = synth.to_uint16(synth.synth_image(torch.from_numpy(mask), len(markers), seed=1))
+    assert int(img.astype(np.int64).sum()) == int(g["image_checksum"][0])          # the generator reproduces the fixture's image
+    mf = tmp_path / "m.txt"
+    mf.write_text("\n".join(markers) + "\n")
+    indices = orc.parse_markers(str(mf), True)
+    assert orc.predicted_panels(indices) == ["immune_extended", "structure"]
+    models = {}
+    for panel in orc.predicted_panels(indices):
+        models[panel] = orc.make_vit(panel)
+        models[panel].load_state_dict(weights.calibrate_head(weights.random_vit_state(panel, seed=2), g[f"meanlogits_{panel}"], 20.0))
+    # the networks on a 300-cell slice keep the CPU suite short; stages 1-3 and 5 run on all 1850 cells
+    img_n = orc.normalize(img, 0.3, 99.8)
+    stats = orc.cell_stats(mask)
+    assert len(stats["ids"]) == 1850 == len(g["labels"])
+    sl = slice(700, 1000)
+    for panel in models:
+        pt, _, _ = orc.build_patches(img_n, mask, indices[panel], stats)
+        np.testing.assert_allclose(orc.vit_probs(models[panel], pt[sl], 128), g[f"probs_{panel}"][sl], rtol=0, atol=2e-6)
+    labels, conf = orc.merge_by_voting({p: g[f"probs_{p}"] for p in models}, 0.3, None)
+    assert labels == g["labels"].tolist()
+    assert np.array_equal(np.array([float(c) for c in conf]), g["conf"])
+    assert orc.unique_cell_types([labels]).tolist() == g["cell_types"].tolist()
