@@ -3,6 +3,9 @@ index range, a single gather of per-cell results at the end.  The re
 distributed code; every rank here holds the whole image and mask and redundantly runs stages 1-2,
 then owns cells [lo, hi) for stages 3-5.  Collectives: all_gather of (label, confidence) and
 all_reduce of the 18 per-type counts - NCCL on GPUs, gloo in the CPU tests.
+A batch of images (the batch-processing CSV) is sharded by image instead: image i belongs to rank i % world
+(`image_owner`), no collective touches the data path, and the owner broadcasts the compact per-cell results at the end
+(`share_image_results`).
 """
 from __future__ import annotations
 
@@ -45,3 +48,32 @@ def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def image_owner(i: int, nranks: int) -> int:
+    """Round-robin image partition of a batch (batch CSV -> images round-robin to GPUs)."""
+    return i % nranks
+
+
+def share_image_results(results: list, device) -> list:
+    """results[i] = (label uint8 (n,), conf float32 (n,), counts int64 (18,)) on the owner rank of image i, None elsewhere.
+    Every rank returns the full list: per image one broadcast of the cell count and one of each array from its owner."""
+    rank, nranks = world()
+    if nranks == 1:
+        return results
+    out = []
+    for i, res in enumerate(results):
+        src = image_owner(i, nranks)
+        n = torch.tensor([res[0].shape[0] if rank == src else 0], dtype=torch.int64, device=device)
+        dist.broadcast(n, src)
+        n = int(n.item())
+        if rank == src:
+            label, conf, counts = (t.to(device).contiguous() for t in res)
+        else:
+            label = torch.empty(n, dtype=torch.uint8, device=device)
+            conf = torch.empty(n, dtype=torch.float32, device=device)
+            counts = torch.empty(18, dtype=torch.int64, device=device)
+        for t in (label, conf, counts):
+            dist.broadcast(t, src)
+        out.append((label, conf, counts))
+    return out

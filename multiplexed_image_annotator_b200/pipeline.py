@@ -13,7 +13,7 @@ import torch
 from . import ops
 from .cell_type_annotation.model import ALL_TYPES, merge_on_device
 from .engine import MaeEngine, VitEngine
-from .parallel import all_gather_rows, all_reduce_sum, shard_range, world
+from .parallel import all_gather_rows, all_reduce_sum, image_owner, shard_range, share_image_results, world
 
 
 @dataclass
@@ -88,3 +88,22 @@ class HotPath:
         if to_host:
             label, conf, counts = label.cpu(), conf.cpu(), counts.cpu()     # D2H ends the step (synchronises)
         return HotPathResult(cells.n, label, conf, counts, probs if keep_probs else {}, cells)
+
+    @torch.no_grad()
+    def run_batch(self, items, to_host: bool = True) -> list:
+        """A batch of (image, mask) pairs (the batch-processing CSV): image i is annotated whole by rank i % world - no
+        collective on the data path - and its owner broadcasts labels / confidences / counts at the end, so every rank
+        returns every image's HotPathResult (cells / probs only on the owner)."""
+        rank, nranks = world()
+        shard_cells, self.shard_cells = self.shard_cells, False
+        try:
+            own = [self.run(img, msk, to_host=False) if image_owner(i, nranks) == rank else None for i, (img, msk) in enumerate(items)]
+        finally:
+            self.shard_cells = shard_cells
+        shared = share_image_results([None if r is None else (r.label, r.confidence, r.counts) for r in own], self.device)
+        out = []
+        for r, (label, conf, counts) in zip(own, shared):
+            if to_host:
+                label, conf, counts = label.cpu(), conf.cpu(), counts.cpu()
+            out.append(HotPathResult(label.shape[0], label, conf, counts, {} if r is None else r.probs, None if r is None else r.cells))
+        return out

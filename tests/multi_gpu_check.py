@@ -37,6 +37,16 @@ assert sharded.n_cells == ref.n_cells
 assert torch.equal(sharded.label, ref.label), "labels differ between sharded and single-rank runs"
 assert torch.equal(sharded.confidence, ref.confidence), "confidences differ"
 assert torch.equal(sharded.counts, ref.counts), "counts differ"
+# batch mode: three images round-robin over the ranks; every rank ends with every image's labels = the single-rank results
+scenes = []
+for k in range(3):
+    m = synth.synth_mask(700 + 100 * k, 900, seed=40 + k, device=dev)
+    scenes.append((torch.from_numpy(synth.to_uint16(synth.synth_image(m, 10, seed=40 + k))).to(dev), m))
+batch = HotPath(idx, {"immune_extended": eng}, device=dev, chunk_cells=1000).run_batch(scenes, to_host=False)
+for (im, m), got in zip(scenes, batch):
+    want = single.run(im, m, to_host=False)
+    assert got.n_cells == want.n_cells and torch.equal(got.label, want.label) and torch.equal(got.confidence, want.confidence)
+    assert torch.equal(got.counts, want.counts)
 ok = torch.ones(1, device=dev)
 dist.all_reduce(ok)
 if rank == 0:

@@ -164,6 +164,17 @@ assert full_c.tolist() == [0.5 * i for i in range(n)]
 assert counts.tolist() == [n, 2]
 mat = parallel.all_gather_rows(torch.full((hi - lo, 3), float(rank)), n, lo, hi)
 assert mat.shape == (n, 3) and mat[:6].eq(0).all() and mat[6:].eq(1).all()
+# batch of 5 "images" sharded round-robin: every rank ends with every image's results
+res = []
+for i in range(5):
+    if parallel.image_owner(i, world) == rank:
+        n_i = 3 + i
+        res.append((torch.full((n_i,), i, dtype=torch.uint8), torch.arange(n_i, dtype=torch.float32) + i, torch.arange(18) * (i + 1)))
+    else:
+        res.append(None)
+full = parallel.share_image_results(res, torch.device("cpu"))
+for i, (l, c, k) in enumerate(full):
+    assert l.tolist() == [i] * (3 + i) and c.tolist() == [float(j + i) for j in range(3 + i)] and k.tolist() == [(i + 1) * j for j in range(18)]
 dist.destroy_process_group()
 print("ok", rank)
 """
