@@ -24,7 +24,7 @@
 //                (cp.reduce.async.bulk.tensor .add.f32), so x is never read into the SM.
 //                TMEM is double-buffered (2 x 256 columns): the epilogue of tile t overlaps the main
 //                loop of tile t+1.  In f16f8 mode the main loop is bound by L2 -> shared-memory delivery
-//                (~6300 B/clk chip-wide; 64 FLOP per L2 byte at 256 x 256 pair tiles), see profiles/r01h_summary.md
+//                (~6300 B/clk chip-wide; 64 FLOP per L2 byte at 256 x 256 pair tiles), see profiles/r01h_experiments.md
 //   CTAs run as PAIRS (cluster of 2, tcgen05 cta_group::2): a pair owns a 256 x BN output tile, each CTA
 //   stages its own 128 rows of A and HALF of the W tile, and the leader CTA issues M = 256 MMAs that read
 //   both CTAs' shared memory.  Per SM this halves the B traffic (L2 -> smem and smem -> tensor core): the
