@@ -104,19 +104,30 @@ def make_scene(size, seed, device, channels=15):
 
 
 def cpu_oracle_rate(img_u16, mask_i32, sd, edge, threads):
-    """cells/sec of the reference algorithm (oracle) on a crop of the workload, host cores only."""
+    """cells/sec of the reference algorithm (oracle) on a crop of the workload, host cores only; the stages are the calls of
+    orc.annotate_image, timed one by one (per-stage CPU rates next to the total)."""
     from oracle import ribca_oracle as orc
-    from multiplexed_image_annotator_b200 import synth
     torch.set_num_threads(threads)
     crop_i = np.ascontiguousarray(img_u16[:, :edge, :edge])
     crop_m = np.ascontiguousarray(mask_i32[:edge, :edge])
     model = orc.make_vit("immune_full")
     model.load_state_dict(sd)
-    indices = {"immune_full": list(range(15))}
-    t0 = time.perf_counter()
-    res = orc.annotate_image(crop_i, crop_m, indices, {"immune_full": model}, bs=128)
-    dt = time.perf_counter() - t0
-    return len(res["labels"]) / dt, res, dt
+    index = list(range(15))
+    t = [time.perf_counter()]
+    img = orc.normalize(crop_i, 0.3, 99.8); t.append(time.perf_counter())
+    stats = orc.cell_stats(crop_m); t.append(time.perf_counter())
+    pt, inten, wins = orc.build_patches(img, crop_m, index, stats, 30); t.append(time.perf_counter())
+    probs = orc.vit_probs(model, pt, 128); t.append(time.perf_counter())
+    labels, conf = orc.merge_by_voting({"immune_full": probs}, 0.3, None); t.append(time.perf_counter())
+    dt = t[-1] - t[0]
+    n = len(labels)
+    mpx_ch = crop_i.shape[0] * edge * edge / 1e6
+    stages = {"1_normalize_ms_per_Mpx_channel": 1e3 * (t[1] - t[0]) / mpx_ch, "2_cell_stats_us_per_pixel": 1e6 * (t[2] - t[1]) / (edge * edge),
+              "3_build_patches_ms_per_cell": 1e3 * (t[3] - t[2]) / max(n, 1), "4_vit_l_ms_per_cell": 1e3 * (t[4] - t[3]) / max(n, 1),
+              "5_merge_us_per_cell": 1e6 * (t[5] - t[4]) / max(n, 1)}
+    # extrapolation to the full workload (15 x 4096^2, n_full cells): labelled as such
+    res = {"labels": labels, "confidence": conf, "probs": {"immune_full": probs}, "stages": stages}
+    return n / dt, res, dt
 
 
 def reference_arm(args):
@@ -310,9 +321,13 @@ def main():
         dprob = float(np.abs(crop.probs[panel].cpu().numpy() - ores["probs"][panel]).max())
         agreement = {"cells": len(ores["labels"]), "label_agreement": same / len(ores["labels"]), "max_abs_dprob": dprob,
                      "labels_present": sorted(set(ores["labels"]))}
+        st = ores["stages"]
+        full_s = (st["1_normalize_ms_per_Mpx_channel"] * 15 * S * S / 1e6 + st["2_cell_stats_us_per_pixel"] * S * S / 1e3
+                  + (st["3_build_patches_ms_per_cell"] + st["4_vit_l_ms_per_cell"]) * n_cells + st["5_merge_us_per_cell"] * n_cells / 1e3) / 1e3
         cpu_baseline = {"value": rate, "unit": "cells/s", "cores": threads, "kind": "port",
                         "sample": f"{edge}x{edge} crop of the same scene, {len(ores['labels'])} cells, {dt:.1f} s, "
-                                  "oracle (numpy/scipy/torch fp32) preprocess+predict"}
+                                  "oracle (numpy/scipy/torch fp32) preprocess+predict",
+                        "stage_rates": st, "extrapolated_full_workload_s": full_s}
 
     # ---- the reference's own GPU path for stage 4 (SURVEY 8d "second baseline"): the oracle's torch modules in eager fp32
     #      on this GPU, bs = 128 slices as cta/model.py:397-406; also the full-population parity check of the step's labels
