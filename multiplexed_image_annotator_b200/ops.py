@@ -98,7 +98,45 @@ def _dptr(arr: np.ndarray):
 # ------------------------------------------------------------------------------------------------
 # stage 1
 # ------------------------------------------------------------------------------------------------
-def normalize(img: torch.Tensor, blur=0.3, amax=99.8, return_stats: bool = False):
+def normalize_from_host(img_host: torch.Tensor, device, blur=0.3, amax=99.8) -> torch.Tensor:
+    """normalize() of a HOST (ideally pinned) stack with the upload hidden behind the kernels: the channels are copied one
+    by one on a side stream and each is normalised as soon as it has arrived (the per-channel statistics of
+    _normalize are independent, reference preprocess.py:218-238)."""
+    if img_host.is_cuda:
+        return normalize(img_host, blur, amax)
+    if img_host.dtype not in _DTYPES:
+        raise TypeError(f"unsupported image dtype {img_host.dtype}")
+    c, h, w = img_host.shape
+    main = torch.cuda.current_stream(device)
+    side = _side_stream(device)
+    raw = torch.empty((c, h, w), dtype=img_host.dtype, device=device)
+    out = torch.empty((c, h, w), dtype=torch.float32, device=device)
+    side.wait_stream(main)                          # `raw` was allocated on the main stream
+    events = []
+    with torch.cuda.stream(side):
+        for k in range(c):
+            raw[k].copy_(img_host[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            events.append(ev)
+    for k in range(c):
+        main.wait_event(events[k])
+        normalize(raw[k:k + 1], blur, amax, out=out[k:k + 1])
+    raw.record_stream(side)
+    return out
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
+
+
+def normalize(img: torch.Tensor, blur=0.3, amax=99.8, return_stats: bool = False, out: torch.Tensor | None = None):
     """ImageProcessor._normalize on the device.  img: (C, H, W) uint8 / uint16 / int32 / float32."""
     _need_cuda(img)
     if img.dtype not in _DTYPES:
@@ -111,7 +149,10 @@ def normalize(img: torch.Tensor, blur=0.3, amax=99.8, return_stats: bool = False
     else:
         w_bl, r_bl = np.zeros(1), -1
     k_lo, k_hi, gamma = percentile_plan(h * w, amax)
-    out = torch.empty((c, h, w), dtype=torch.float32, device=img.device)
+    if out is None:
+        out = torch.empty((c, h, w), dtype=torch.float32, device=img.device)
+    elif out.shape != img.shape or out.dtype != torch.float32 or not out.is_contiguous() or not img.is_contiguous():
+        raise ValueError("normalize: `out` must be a contiguous float32 tensor of the image's shape")
     stats = torch.empty((c, 4), dtype=torch.float32, device=img.device)
     ws_bytes = L.ribca_normalize_workspace_bytes(c, h, w)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)

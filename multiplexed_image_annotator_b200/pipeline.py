@@ -55,14 +55,18 @@ class HotPath:
 
     @torch.no_grad()
     def run(self, image, mask, to_host: bool = True, keep_probs: bool = False) -> HotPathResult:
-        img = self._to_device(image)
         msk = self._to_device(mask)
         if msk.dtype != torch.int32:
             msk = msk.to(torch.int32)
-        if self.normalization:
-            img = ops.normalize(img, self.blur, self.amax)
-        elif img.dtype != torch.float32:
-            img = img.to(torch.float32)
+        host_img = torch.from_numpy(image) if isinstance(image, np.ndarray) else image
+        if self.normalization and not host_img.is_cuda:
+            img = ops.normalize_from_host(host_img, self.device, self.blur, self.amax)     # upload hidden behind stage 1
+        else:
+            img = self._to_device(host_img)
+            if self.normalization:
+                img = ops.normalize(img, self.blur, self.amax)
+            elif img.dtype != torch.float32:
+                img = img.to(torch.float32)
         cells = ops.cell_stats(msk)
         mn = ops.channel_min(img)
         rank, nranks = world() if self.shard_cells else (0, 1)

@@ -324,3 +324,15 @@ def test_neighbourhood_matrix_and_compositions_match_the_reference_loops(tmp_pat
     assert text[1] == "T0," + "".join(f"{v:.3f}," for v in m[0])
     with pytest.raises(ValueError):
         ops.knn_2d(torch.from_numpy(xy[:10]).to(DEV), 25)                     # sklearn: n_neighbors > n_samples
+
+
+def test_normalize_from_host_overlapped_upload_is_identical():
+    """The e2e entry uploads the stack channel by channel on a side stream and normalises each channel as it arrives:
+    same bits as normalising the resident stack (per-channel statistics are independent)."""
+    mask = synth.synth_mask(300, 260, seed=4)
+    img = torch.from_numpy(synth.to_uint16(synth.synth_image(mask, 5, seed=4)))
+    want = ops.normalize(img.to(DEV), 0.3, 99.8)
+    for host in (img, img.pin_memory()):
+        got = ops.normalize_from_host(host, torch.device(DEV, torch.cuda.current_device()), 0.3, 99.8)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)

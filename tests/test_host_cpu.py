@@ -42,6 +42,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     if "UTCHMMA" not in sass:               # -fun needs the mangled name on some toolkits: fall back to everything
         sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "UTCQMMA" in sass                # the e4m3 pass of the default f16f8 operand format (kind::f8f6f4)
 
 
 def test_ops_refuse_cpu_tensors():
