@@ -179,8 +179,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the communicator is created,
+        # so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     L = _lib.lib()
 
     # ---- workload: one synthetic scene per rank, host copy in pinned memory ----------------------------
