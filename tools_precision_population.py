@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Full-population precision check on the bench scene: probabilities of every cell from the f16f8 and bf16x3 engines and
-from the reference modules in eager fp32, all against the same modules in fp64 (ground truth).  usage: tools_precision_population.py [size]"""
+from the reference modules in eager fp32, all against the same modules in fp64 (ground truth).
+usage: tools_precision_population.py [size] [panel]"""
 import json, sys, torch, numpy as np
 sys.path.insert(0, ".")
 from multiplexed_image_annotator_b200 import engine, ops, synth, weights
@@ -8,9 +9,11 @@ from multiplexed_image_annotator_b200.cell_type_annotation.model import merge_on
 from oracle import ribca_oracle as orc
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 dev = torch.device("cuda", 0)
-panel, index = "immune_full", list(range(15))
+panel = sys.argv[2] if len(sys.argv) > 2 else "immune_full"
+n_ch = weights.VIT_SPECS[panel].in_chans
+index = list(range(n_ch))
 mask = synth.synth_mask(S, S, grid=18, seed=2, device=dev)
-img = torch.from_numpy(synth.to_uint16(synth.synth_image(mask, 15, seed=2))).to(dev)
+img = torch.from_numpy(synth.to_uint16(synth.synth_image(mask, n_ch, seed=2))).to(dev)
 norm = ops.normalize(img, 0.3, 99.8)
 cells = ops.cell_stats(mask)
 mn = ops.channel_min(norm)
@@ -34,7 +37,7 @@ with torch.no_grad():
 P = {k: torch.cat(v) for k, v in out.items()}
 truth = P["fp64"]
 lab = {k: merge_on_device({panel: v.float()}, 0.3, None)[0] for k, v in P.items()}
-res = {"cells": cells.n}
+res = {"cells": cells.n, "panel": panel}
 for k in ("fp32", "bf16x3", "f16f8"):
     d = (P[k] - truth).abs().max(1).values
     res[k] = {"max": d.max().item(), "p99.99": d.quantile(0.9999).item(), "p99.9": d.quantile(0.999).item(), "p99": d.quantile(0.99).item(),
