@@ -190,3 +190,33 @@ def test_two_rank_gather_over_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in out, out
+
+
+def test_f16f8_weight_scale_keeps_every_plane_finite():
+    """t of the f16f8 weight packing: max|w| * 2^t <= 128 < 448 (e4m3 copies) and max|w| * 2^(t+8) <= 32768 < 65504 (fp16 plane)."""
+    for m in (1e-6, 3e-4, 0.02, 0.1, 0.99, 1.0, 1.01, 7.5, 128.0, 300.0, 5e4):
+        t = ops.weight_log2_scale(m)
+        if -20 < t < 30:                                   # inside the clamp the bound is tight within a factor of two
+            assert 64.0 < m * 2.0 ** t <= 128.0, (m, t)
+        assert m * 2.0 ** (t + 8) <= 32768.0 or t == -20
+    assert ops.weight_log2_scale(0.1) == 10 and ops.weight_log2_scale(1.0) == 7
+    assert ops.weight_log2_scale(0.0) == 0 and ops.weight_log2_scale(float("inf")) == 0 and ops.weight_log2_scale(float("nan")) == 0
+    assert ops.plane_format("f16f8") == ops.FMT_F16F8 and ops.plane_format("bf16x3") == ops.FMT_BF16 == ops.plane_format("simt")
+
+
+def test_precision_emulation_of_the_operand_formats():
+    """The error model behind the default precision, on the CPU: a.w from (fp16 a_hi, e4m3 pairs) operands is within
+    2^-14 of sum|a||w| of the exact product, bf16 {hi, lo} within 2^-15, and a single fp16 pass is ~50x worse."""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn((64, 576), generator=g, dtype=torch.float64)
+    w = torch.randn((96, 576), generator=g, dtype=torch.float64) * 0.05
+    exact, bound = a @ w.T, a.abs() @ w.abs().T
+    e4 = lambda x: x.clamp(-448, 448).float().to(torch.float8_e4m3fn).double()
+    t = ops.weight_log2_scale(float(w.abs().max()))
+    ah, wh = a.half().double(), w.half().double()
+    f16f8 = (ah @ (wh * 2.0 ** (t + 8)).T + e4((a - ah) * 256) @ e4(wh * 2.0 ** t).T + e4(ah) @ e4((w - wh) * 2.0 ** (t + 8)).T) * 2.0 ** -(t + 8)
+    bh, vh = a.bfloat16().double(), w.bfloat16().double()
+    bl, vl = (a - bh).bfloat16().double(), (w - vh).bfloat16().double()
+    bf16x3 = bl @ vh.T + bh @ vl.T + bh @ vh.T
+    r8, r3, r1 = (((x - exact).abs() / bound).max().item() for x in (f16f8, bf16x3, ah @ wh.T))
+    assert r8 < 2.0 ** -14 and r3 < 2.0 ** -15 and r1 > 20 * r8, (r8, r3, r1)
