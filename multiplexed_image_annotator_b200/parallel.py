@@ -1,6 +1,7 @@
 """Multi-GPU partitioning: one process per GPU (torch.distributed), cells sharded by contiguous
 index range, a single gather of per-cell results at the end.  The reference has no
-distributed code; every rank here holds the whole image and mask and redundantly runs stages 1-2,
+distributed code; every rank here ends up with the whole normalised image (stage 1 is split by channel and the
+planes are broadcast, pipeline.HotPath._normalize_sharded) and the mask, runs stage 2 redundantly (1 ms),
 then owns cells [lo, hi) for stages 3-5.  Collectives: all_gather of (label, confidence) and
 all_reduce of the 18 per-type counts - NCCL on GPUs, gloo in the CPU tests.
 A batch of images (the batch-processing CSV) is sharded by image instead: image i belongs to rank i % world

@@ -36,17 +36,33 @@ class HotPath:
 
     def __init__(self, panels: dict, models: dict, imputers: dict | None = None, *, normalization=True, blur=0.3,
                  amax=99.8, confidence=0.3, cell_type_confidence=None, chunk_cells=4096, device="cuda",
-                 shard_cells=True, cell_size=30):
+                 shard_cells=True, cell_size=30, shard_stage1=True):
         self.panels, self.models, self.imputers = dict(panels), models, imputers or {}
         self.normalization, self.blur, self.amax = normalization, blur, amax
         self.confidence, self.ctc = confidence, cell_type_confidence
         self.chunk = chunk_cells
         self.device = torch.device(device)
         self.shard_cells = shard_cells
+        self.shard_stage1 = shard_stage1          # with shard_cells and > 1 rank: channels of stage 1 split over the ranks
         self.cell_size = cell_size
         for p in self.panels:
             if not isinstance(models.get(p), VitEngine):
                 raise ValueError(f"no classifier engine for panel {p}")
+
+    def _normalize_sharded(self, image, rank, nranks):
+        """Stage 1 of ONE image shared by the ranks: its channels are independent (reference preprocess.py:218-238), so rank r
+        uploads and normalises channels c = r (mod N) only and each finished float32 plane is broadcast over NVLink from its
+        owner - instead of every rank uploading and normalising the whole stack.  Same kernel on the same data: bit-identical."""
+        import torch.distributed as dist
+        c, h, w = image.shape
+        out = torch.empty((c, h, w), dtype=torch.float32, device=self.device)
+        for k in range(rank, c, nranks):
+            plane = image[k:k + 1]
+            plane = plane.to(self.device, non_blocking=True) if not plane.is_cuda else plane.contiguous()
+            ops.normalize(plane, self.blur, self.amax, out=out[k:k + 1])
+        for k in range(c):
+            dist.broadcast(out[k], src=k % nranks)
+        return out
 
     def _to_device(self, a):
         if isinstance(a, np.ndarray):
@@ -59,7 +75,10 @@ class HotPath:
         if msk.dtype != torch.int32:
             msk = msk.to(torch.int32)
         host_img = torch.from_numpy(image) if isinstance(image, np.ndarray) else image
-        if self.normalization and not host_img.is_cuda:
+        rank, nranks = world() if self.shard_cells else (0, 1)
+        if self.normalization and nranks > 1 and self.shard_stage1:
+            img = self._normalize_sharded(host_img, rank, nranks)
+        elif self.normalization and not host_img.is_cuda:
             img = ops.normalize_from_host(host_img, self.device, self.blur, self.amax)     # upload hidden behind stage 1
         else:
             img = self._to_device(host_img)
@@ -69,7 +88,6 @@ class HotPath:
                 img = img.to(torch.float32)
         cells = ops.cell_stats(msk)
         mn = ops.channel_min(img)
-        rank, nranks = world() if self.shard_cells else (0, 1)
         lo, hi = shard_range(cells.n, rank, nranks)
         names = list(self.panels)
         idx = [self.panels[p] for p in names]
