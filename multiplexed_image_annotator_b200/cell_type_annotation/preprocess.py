@@ -197,12 +197,16 @@ class ImageProcessor(object):
         for i, (image_path, mask_path) in enumerate(zip(self.image_paths, self.mask_paths)):
             image = read_image(image_path)
             mask = read_mask(mask_path)                       # 2-D, int32 (preprocess.py:246-250)
-            img_dev = torch.from_numpy(image).to(self.device, non_blocking=True)
             mask_dev = torch.from_numpy(mask).to(self.device, non_blocking=True)
-            if self.normalization:
-                img_dev = ops.normalize(img_dev, self.blur, self.amax)
-            elif img_dev.dtype != torch.float32:
-                img_dev = img_dev.to(torch.float32)
+            if self.normalization and nranks > 1:
+                from ..pipeline import normalize_over_ranks          # channels split over the ranks, planes broadcast
+                img_dev = normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks)
+            elif self.normalization:
+                img_dev = ops.normalize_from_host(torch.from_numpy(image), self.device, self.blur, self.amax)
+            else:
+                img_dev = torch.from_numpy(image).to(self.device, non_blocking=True)
+                if img_dev.dtype != torch.float32:
+                    img_dev = img_dev.to(torch.float32)
             self.masks.append(mask)
             tab = ops.cell_stats(mask_dev)
             self.images_dev.append(img_dev)

@@ -29,6 +29,24 @@ class HotPathResult:
         return [ALL_TYPES[k] for k in self.label.cpu().tolist()]
 
 
+def normalize_over_ranks(image, device, blur, amax, rank, nranks) -> torch.Tensor:
+    """Stage 1 of ONE image shared by the ranks: its channels are independent (reference preprocess.py:218-238), so rank r
+    uploads and normalises channels c = r (mod N) only and each finished float32 plane is broadcast over NVLink from its
+    owner - instead of every rank uploading and normalising the whole stack.  Same kernel on the same data: bit-identical."""
+    import torch.distributed as dist
+    if isinstance(image, np.ndarray):
+        image = torch.from_numpy(image)
+    c, h, w = image.shape
+    out = torch.empty((c, h, w), dtype=torch.float32, device=device)
+    for k in range(rank, c, nranks):
+        plane = image[k:k + 1]
+        plane = plane.to(device, non_blocking=True) if not plane.is_cuda else plane.contiguous()
+        ops.normalize(plane, blur, amax, out=out[k:k + 1])
+    for k in range(c):
+        dist.broadcast(out[k], src=k % nranks)
+    return out
+
+
 class HotPath:
     """Stages 1-5 for one image.  `panels` maps panel name -> channel index list (MarkerParser.indices
     restricted to the panels that predict consumes); `models` maps panel -> VitEngine; `imputers`
@@ -50,19 +68,7 @@ class HotPath:
                 raise ValueError(f"no classifier engine for panel {p}")
 
     def _normalize_sharded(self, image, rank, nranks):
-        """Stage 1 of ONE image shared by the ranks: its channels are independent (reference preprocess.py:218-238), so rank r
-        uploads and normalises channels c = r (mod N) only and each finished float32 plane is broadcast over NVLink from its
-        owner - instead of every rank uploading and normalising the whole stack.  Same kernel on the same data: bit-identical."""
-        import torch.distributed as dist
-        c, h, w = image.shape
-        out = torch.empty((c, h, w), dtype=torch.float32, device=self.device)
-        for k in range(rank, c, nranks):
-            plane = image[k:k + 1]
-            plane = plane.to(self.device, non_blocking=True) if not plane.is_cuda else plane.contiguous()
-            ops.normalize(plane, self.blur, self.amax, out=out[k:k + 1])
-        for k in range(c):
-            dist.broadcast(out[k], src=k % nranks)
-        return out
+        return normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks)
 
     def _to_device(self, a):
         if isinstance(a, np.ndarray):

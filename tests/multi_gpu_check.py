@@ -47,6 +47,27 @@ for (im, m), got in zip(scenes, batch):
     want = single.run(im, m, to_host=False)
     assert got.n_cells == want.n_cells and torch.equal(got.label, want.label) and torch.equal(got.confidence, want.confidence)
     assert torch.equal(got.counts, want.counts)
+# the reference-shaped Annotator under 2 ranks (stage 1 split by channel, cells split by range): same labels as one rank
+import tempfile
+import numpy as np
+from multiplexed_image_annotator_b200.cell_type_annotation import model as bmodel
+from multiplexed_image_annotator_b200.cell_type_annotation.markerParse import MarkerParser
+with tempfile.TemporaryDirectory() as tmp:
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        np.save("img.npy", img.cpu().numpy()); np.save("mask.npy", mask.cpu().numpy())
+        synth.write_marker_file("markers.txt", list(MarkerParser(strict=True).panels["immune_extended"]))
+        with open("images.csv", "w") as f:
+            f.write("image_path,mask_path\nimg.npy,mask.npy\n")
+        cal_sd = dict(sd); cal_sd["head.weight"], cal_sd["head.bias"] = cal["head.weight"], cal["head.bias"]
+        bmodel.register_state("immune_extended", cal_sd)
+        ann = bmodel.Annotator("markers.txt", "images.csv", "cuda", "./", "mg", True, True, -1, True, 0.3, 99.8, 0.3, 30, None, n_jobs=0)
+        ann.preprocess()
+        ann.predict(128)
+        assert np.array_equal(ann.labels_index[0], ref.label.cpu().numpy()), "Annotator labels differ under 2 ranks"
+    finally:
+        os.chdir(cwd)
 ok = torch.ones(1, device=dev)
 dist.all_reduce(ok)
 if rank == 0:
