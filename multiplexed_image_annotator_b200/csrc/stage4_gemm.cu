@@ -65,6 +65,9 @@ constexpr int kStagingTile = 4096;            // 32 rows x 128 B (fp32 x 32 cols
 constexpr int kStagingBytes = kStagingBufs * kStagingTile; // per epilogue warp
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
+#ifndef RIBCA_OPERAND_L2_PROMOTION
+#define RIBCA_OPERAND_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B      // A/B-tested against 128B and NONE: no difference
+#endif
 // (register allocation is per 4 warps: 14 warps -> 16 x 32 x 128 registers; 18 warps would be capped at 96)
 #define RIBCA_GEMM_BOUNDS __launch_bounds__(kGemmThreads, 1)
 
@@ -453,7 +456,7 @@ static int make_operand_map(CUtensorMap* map, const void* base, long long plane_
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)n_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, RIBCA_OPERAND_L2_PROMOTION,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d box_rows=%d plane=%lld", (int)r, rows, K, box_rows, plane_elems);
