@@ -19,7 +19,7 @@ import pandas as pd
 import torch
 
 from .. import ops
-from ..io import read_image, read_mask
+from ..io import is_tiff, iter_tiff_planes, read_image, read_mask
 from ..parallel import shard_range, world
 from .markerImputer import MarkerImputer
 
@@ -195,10 +195,18 @@ class ImageProcessor(object):
     def transform(self):
         rank, nranks = world()
         for i, (image_path, mask_path) in enumerate(zip(self.image_paths, self.mask_paths)):
-            image = read_image(image_path)
             mask = read_mask(mask_path)                       # 2-D, int32 (preprocess.py:246-250)
             mask_dev = torch.from_numpy(mask).to(self.device, non_blocking=True)
-            if self.normalization and nranks > 1:
+            img_dev = None
+            if self.normalization and nranks == 1 and is_tiff(image_path):
+                try:                                          # decode, upload and stage 1 overlapped plane by plane
+                    img_dev = ops.normalize_from_planes(iter_tiff_planes(image_path), self.device, self.blur, self.amax)
+                except (ValueError, KeyError):
+                    img_dev = None                            # a TIFF flavour the reader does not take: whole-file decode below
+            image = read_image(image_path) if img_dev is None else None
+            if img_dev is not None:
+                pass
+            elif self.normalization and nranks > 1:
                 from ..pipeline import normalize_over_ranks          # channels split over the ranks, planes broadcast
                 img_dev = normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks)
             elif self.normalization:

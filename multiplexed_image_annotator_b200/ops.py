@@ -126,6 +126,35 @@ def normalize_from_host(img_host: torch.Tensor, device, blur=0.3, amax=99.8) -> 
     return out
 
 
+def normalize_from_planes(planes, device, blur=0.3, amax=99.8) -> torch.Tensor:
+    """normalize() fed by a decoder: `planes` yields (k, host stack (C, H, W)) as soon as plane k of the (pinned) stack is
+    complete (io.iter_tiff_planes).  Plane k is uploaded on the side stream and normalised while the decoder reads plane k + 1:
+    disk read, H2D copy and stage 1 overlap."""
+    main = torch.cuda.current_stream(device)
+    side = _side_stream(device)
+    raw = out = None
+    for k, stack in planes:
+        host = torch.from_numpy(stack) if isinstance(stack, np.ndarray) else stack
+        if host.dtype not in _DTYPES:
+            host = host.to(torch.float32)
+        if raw is None:
+            c, h, w = host.shape
+            raw = torch.empty((c, h, w), dtype=host.dtype, device=device)
+            out = torch.empty((c, h, w), dtype=torch.float32, device=device)
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            raw[k].copy_(host[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        main.wait_event(ev)
+        normalize(raw[k:k + 1], blur, amax, out=out[k:k + 1])
+    if raw is None:
+        raise ValueError("normalize_from_planes: the decoder produced no plane")
+    side.synchronize()            # only copies run there: the decoder may release its (pinned) buffer once this returns
+    raw.record_stream(side)
+    return out
+
+
 _SIDE = {}
 
 

@@ -425,6 +425,16 @@ def test_cli_run_and_gui_api_full_sequence(tmp_path, monkeypatch):
     inten, names = gui_api.gui_api("work")
     rows = open("results/single_run_annotation_0.csv").read().strip().split("\n")
     assert {r.split(",")[-1] for r in rows[1:]} <= {"Region 0", "Region 1"}
+    # the same image as a multi-page TIFF + TIFF mask goes through the streaming decoder (decode / upload / stage 1 overlapped
+    # plane by plane) and gives the same CSV as the .npy input
+    from PIL import Image
+    stack = np.load("s1_img.npy")
+    ims = [Image.fromarray(p) for p in stack]
+    ims[0].save("s1.tif", save_all=True, append_images=ims[1:])
+    Image.fromarray(np.load("s1_mask.npy").astype(np.int32)).save("s1_mask.tif")
+    cli.run("markers.txt", "s1.tif", "s1_mask.tif", "cuda", "./", "tif", 64, True, True, -1, 0, True, 0.3, 99.8, 0.3, 30, ctc, 0)
+    cli.run("markers.txt", "s1_img.npy", "s1_mask.npy", "cuda", "./", "npy", 64, True, True, -1, 0, True, 0.3, 99.8, 0.3, 30, ctc, 0)
+    assert open("results/tif_annotation_0.csv").read() == open("results/npy_annotation_0.csv").read()
 
 
 def test_c1_reference_example_configuration(golden_dir, tmp_path, monkeypatch):

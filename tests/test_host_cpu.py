@@ -220,3 +220,111 @@ def test_precision_emulation_of_the_operand_formats():
     bf16x3 = bl @ vh.T + bh @ vl.T + bh @ vh.T
     r8, r3, r1 = (((x - exact).abs() / bound).max().item() for x in (f16f8, bf16x3, ah @ wh.T))
     assert r8 < 2.0 ** -14 and r3 < 2.0 ** -15 and r1 > 20 * r8, (r8, r3, r1)
+
+
+# ------------------------------------------------------------------------------------------------
+# the TIFF reader of io.py: classic / Big, both byte orders, strips / tiles, codec fallback, OME names
+# ------------------------------------------------------------------------------------------------
+def _write_tiff(path, pages, big=False, bo="<", tile=None, description=None):
+    """Minimal uncompressed TIFF / BigTIFF writer for the tests: one IFD per 2-D page, strips of 7 rows or `tile` x `tile` tiles."""
+    import struct
+    off_fmt, cnt_fmt, ent = ("Q", "Q", "HHQQ") if big else ("I", "H", "HHII")
+    osz = 8 if big else 4
+    blob = bytearray(b"II" if bo == "<" else b"MM")
+    blob += struct.pack(bo + "H", 43 if big else 42)
+    blob += struct.pack(bo + "HHQ", 8, 0, 0) if big else struct.pack(bo + "I", 0)
+    first_ptr = len(blob) - osz
+    prev_ptr = first_ptr
+    for arr in pages:
+        a = np.ascontiguousarray(arr.astype(arr.dtype.newbyteorder(bo)))
+        h, w = a.shape
+        chunks = []
+        if tile:
+            for y in range(0, h, tile):
+                for x in range(0, w, tile):
+                    t = np.zeros((tile, tile), a.dtype)
+                    t[:min(tile, h - y), :min(tile, w - x)] = a[y:y + tile, x:x + tile]
+                    chunks.append(t.tobytes())
+        else:
+            chunks = [a[y:y + 7].tobytes() for y in range(0, h, 7)]
+        offs = []
+        for ch in chunks:
+            offs.append(len(blob)); blob += ch
+        fmt = {"u": 1, "i": 2, "f": 3}[a.dtype.kind]
+        tags = [(256, 4, [w]), (257, 4, [h]), (258, 3, [a.dtype.itemsize * 8]), (259, 3, [1]), (262, 3, [1]), (277, 3, [1]), (339, 3, [fmt])]
+        tags += [(322, 4, [tile]), (323, 4, [tile]), (324, 16 if big else 4, offs), (325, 16 if big else 4, [len(c) for c in chunks])] if tile else \
+                [(278, 4, [7]), (273, 16 if big else 4, offs), (279, 16 if big else 4, [len(c) for c in chunks])]
+        if description is not None:
+            tags.append((270, 2, description.encode() + b"\0"))
+        tags.sort()
+        # out-of-line values first
+        vals = {}
+        for tag, typ, v in tags:
+            code = {2: "c", 3: "H", 4: "I", 16: "Q"}[typ]
+            data = bytes(v) if typ == 2 else struct.pack(bo + code * len(v), *v)
+            if len(data) > osz:
+                if len(blob) % 2: blob += b"\0"
+                vals[tag] = (len(blob), None); blob += data
+            else:
+                vals[tag] = (None, data.ljust(osz, b"\0"))
+        if len(blob) % 2: blob += b"\0"
+        ifd = len(blob)
+        blob[prev_ptr:prev_ptr + osz] = struct.pack(bo + off_fmt, ifd)
+        blob += struct.pack(bo + cnt_fmt, len(tags))
+        for tag, typ, v in tags:
+            pos, inline = vals[tag]
+            blob += struct.pack(bo + "HH", tag, typ) + struct.pack(bo + off_fmt, len(v))
+            blob += struct.pack(bo + off_fmt, pos) if pos is not None else inline
+        prev_ptr = len(blob)
+        blob += struct.pack(bo + off_fmt, 0)
+    open(path, "wb").write(bytes(blob))
+
+
+@pytest.mark.parametrize("big,bo,tile,dtype", [(False, "<", None, np.uint16), (False, ">", None, np.uint16), (True, "<", 16, np.float32),
+                                               (True, ">", 16, np.int32), (False, "<", 32, np.uint8)])
+def test_tiff_reader_uncompressed_layouts(tmp_path, big, bo, tile, dtype):
+    from multiplexed_image_annotator_b200 import io as bio
+    rng = np.random.default_rng(3)
+    stack = (rng.random((4, 37, 53)) * 60000).astype(dtype)
+    path = str(tmp_path / "s.tif")
+    _write_tiff(path, list(stack), big=big, bo=bo, tile=tile)
+    tf = bio.TiffFile(path)
+    assert tf.big == big and len(tf.pages) == 4 and all(p.raw_readable and p.tiled == bool(tile) for p in tf.pages)
+    got = bio.read_tiff_stack(path, pin=False)
+    assert got.dtype == np.dtype(dtype) and np.array_equal(got, stack)
+    assert np.array_equal(bio.read_image(path), stack if dtype != np.float64 else stack.astype(np.float32))
+
+
+def test_tiff_reader_matches_pil_and_falls_back_for_codecs(tmp_path):
+    from PIL import Image, features
+    from multiplexed_image_annotator_b200 import io as bio
+    rng = np.random.default_rng(4)
+    stack = (rng.random((5, 40, 64)) * 65535).astype(np.uint16)
+    ims = [Image.fromarray(p) for p in stack]
+    raw = str(tmp_path / "raw.tif")
+    ims[0].save(raw, save_all=True, append_images=ims[1:])
+    assert all(p.raw_readable for p in bio.TiffFile(raw).pages)
+    assert np.array_equal(bio.read_tiff_stack(raw, pin=False), stack)
+    if features.check("libtiff"):
+        for comp in ("tiff_lzw", "tiff_adobe_deflate"):
+            f = str(tmp_path / f"{comp}.tif")
+            ims[0].save(f, save_all=True, append_images=ims[1:], compression=comp)
+            assert not bio.TiffFile(f).pages[0].raw_readable
+            assert np.array_equal(bio.read_tiff_stack(f, pin=False), stack)          # decoded page by page through PIL
+    # a single-page TIFF mask comes back 2-D (imread semantics), an RGB-like PNG mask keeps its first channel
+    Image.fromarray(stack[0]).save(str(tmp_path / "m.tif"))
+    assert bio.read_mask(str(tmp_path / "m.tif")).shape == (40, 64)
+    Image.fromarray(np.stack([stack[0] >> 8] * 3, -1).astype(np.uint8)).save(str(tmp_path / "m.png"))
+    assert np.array_equal(bio.read_mask(str(tmp_path / "m.png")), (stack[0] >> 8).astype(np.int32))
+
+
+def test_ome_channel_names(tmp_path):
+    from multiplexed_image_annotator_b200 import io as bio
+    xml = ('<?xml version="1.0" encoding="UTF-8"?><OME xmlns="http://www.openmicroscopy.org/Schemas/OME/2016-06"><Image ID="Image:0">'
+           '<Pixels ID="Pixels:0" SizeC="3"><Channel ID="Channel:0:0" Name="DAPI"/><Channel ID="Channel:0:1" Name="CD45"/>'
+           '<Channel ID="Channel:0:2"/><Channel ID="Channel:0:3" Name="PanCK"/></Pixels></Image></OME>')
+    path = str(tmp_path / "o.ome.tif")
+    _write_tiff(path, [np.zeros((8, 8), np.uint16)] * 3, description=xml)
+    assert bio.ome_channel_names(path) == ["DAPI", "CD45", "PanCK"]
+    _write_tiff(path, [np.zeros((8, 8), np.uint16)], description="not xml")
+    assert bio.ome_channel_names(path) is None
