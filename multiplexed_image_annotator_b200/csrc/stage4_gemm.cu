@@ -40,10 +40,13 @@
 namespace ribca {
 
 constexpr int BM = 128;
-constexpr int BK = 32;              // 32 bf16 = 64 bytes = one SWIZZLE_64B row
+#ifndef RIBCA_BK
+#define RIBCA_BK 64
+#endif
+constexpr int BK = RIBCA_BK;        // 16-bit elements per K block: 32 = one SWIZZLE_64B row (64 bytes), 64 = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 #ifndef RIBCA_STAGES
-#define RIBCA_STAGES 6
+#define RIBCA_STAGES (RIBCA_BK == 64 ? 3 : 6)
 #endif
 constexpr int kStages = RIBCA_STAGES;
 #ifndef RIBCA_EPI_WARPS
@@ -70,6 +73,11 @@ constexpr int kTmemCols = 512;
 #endif
 // (register allocation is per 4 warps: 14 warps -> 16 x 32 x 128 registers; 18 warps would be capped at 96)
 #define RIBCA_GEMM_BOUNDS __launch_bounds__(kGemmThreads, 1)
+
+// shared-memory matrix descriptor of an operand tile whose rows are BK 16-bit elements
+__device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t smem_addr) {
+  return BK == 64 ? make_smem_desc(smem_addr) : make_smem_desc_sw64(smem_addr);
+}
 
 struct GemmEpilogue {
   const float* bias;        // [N] or null
@@ -327,10 +335,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // then the fp16 planes; one accumulator, one instruction descriptor (format code 0 = E4M3 = F16)
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t a_0 = make_smem_desc_sw64(a_addr + k * UMMA_K * 2);
-              const uint64_t a_1 = make_smem_desc_sw64(a_addr + kATile + k * UMMA_K * 2);
-              const uint64_t w_0 = make_smem_desc_sw64(b_addr + k * UMMA_K * 2);
-              const uint64_t w_1 = make_smem_desc_sw64(b_addr + w_tile + k * UMMA_K * 2);
+              const uint64_t a_0 = make_smem_desc_k(a_addr + k * UMMA_K * 2);
+              const uint64_t a_1 = make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2);
+              const uint64_t w_0 = make_smem_desc_k(b_addr + k * UMMA_K * 2);
+              const uint64_t w_1 = make_smem_desc_k(b_addr + w_tile + k * UMMA_K * 2);
               umma_e4m3_2sm(d_tmem, a_1, w_1, idesc, (it > 0 || k > 0) ? 1u : 0u);
               umma_bf16_2sm(d_tmem, a_0, w_0, idesc, 1u);
             }
@@ -338,10 +346,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // lo.hi + hi.lo + hi.hi from the four staged tiles
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t a_hi = make_smem_desc_sw64(a_addr + k * UMMA_K * 2);
-              const uint64_t a_lo = make_smem_desc_sw64(a_addr + kATile + k * UMMA_K * 2);
-              const uint64_t w_hi = make_smem_desc_sw64(b_addr + k * UMMA_K * 2);
-              const uint64_t w_lo = make_smem_desc_sw64(b_addr + w_tile + k * UMMA_K * 2);
+              const uint64_t a_hi = make_smem_desc_k(a_addr + k * UMMA_K * 2);
+              const uint64_t a_lo = make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2);
+              const uint64_t w_hi = make_smem_desc_k(b_addr + k * UMMA_K * 2);
+              const uint64_t w_lo = make_smem_desc_k(b_addr + w_tile + k * UMMA_K * 2);
               umma_bf16_2sm(d_tmem, a_lo, w_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
               umma_bf16_2sm(d_tmem, a_hi, w_lo, idesc, 1u);
               umma_bf16_2sm(d_tmem, a_hi, w_hi, idesc, 1u);
@@ -349,7 +357,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16_2sm(d_tmem, make_smem_desc_sw64(a_addr + k * UMMA_K * 2), make_smem_desc_sw64(b_addr + k * UMMA_K * 2),
+              umma_bf16_2sm(d_tmem, make_smem_desc_k(a_addr + k * UMMA_K * 2), make_smem_desc_k(b_addr + k * UMMA_K * 2),
                             idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm_mcast(&empty_bar[stage], (uint16_t)0x3);   // slot reusable in both CTAs once these MMAs retire
@@ -456,7 +464,7 @@ static int make_operand_map(CUtensorMap* map, const void* base, long long plane_
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)n_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, RIBCA_OPERAND_L2_PROMOTION,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, RIBCA_OPERAND_L2_PROMOTION,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d box_rows=%d plane=%lld", (int)r, rows, K, box_rows, plane_elems);
