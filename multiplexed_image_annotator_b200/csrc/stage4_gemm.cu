@@ -58,12 +58,12 @@ constexpr int kEpiPerQuad = kEpiWarps / 4;
 #ifndef RIBCA_STAGING_BUFS
 #define RIBCA_STAGING_BUFS 1
 #endif
-constexpr int kStagingBufs = RIBCA_STAGING_BUFS;      // per-warp staging tiles (shared memory budget: 1 with 12+ warps)
+constexpr int kStagingBufs = RIBCA_STAGING_BUFS;      // per-warp staging tiles (1: the ring takes 192 of the 227 KB)
 constexpr int kMaxBN = 256;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
-constexpr int kATile = BM * BK * 2;             // one plane of A:  8 KB
-constexpr int kABytes = 2 * kATile;             // hi + lo:        16 KB
-constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, hi + lo: 16 KB
+constexpr int kATile = BM * BK * 2;             // one plane of A:  16 KB at BK = 64
+constexpr int kABytes = 2 * kATile;             // both planes:    32 KB
+constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, both planes: 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kStagingTile = 4096;            // 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo tiles)
 constexpr int kStagingBytes = kStagingBufs * kStagingTile; // per epilogue warp
@@ -455,7 +455,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n, __nv
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// 3-D map over a split operand: dims (K, rows, 2 planes), box (32, box_rows, n_planes), 64B swizzle
+// 3-D map over a two-plane operand: dims (K, rows, 2 planes), box (BK, box_rows, n_planes), rows of BK * 2 bytes swizzled
 static int make_operand_map(CUtensorMap* map, const void* base, long long plane_elems, int rows, int K, int box_rows,
                             int n_planes) {
   auto encode = tensor_map_encode_fn();
