@@ -3,10 +3,9 @@
 A numpy / scipy / plain-torch restatement of the reference algorithm (sun-huangqingbo/
 multiplexed-image-annotator), each function citing the reference file:line it follows
 (paths relative to the reference root; `cta/` = src/multiplexed_image_annotator/cell_type_annotation/).
-Only `tests/`, `__graft_entry__.smoke()`, `bench.py`'s baseline legs (CPU baseline, `--impl reference`, and the
-reference-GPU-path baseline that runs these torch modules in eager fp32 as the checker of the full population) and the
-measurement scripts `tools_*.py` may import this module; the product package never does (it fails loudly without its
-CUDA library).
+Only `tests/` (incl. its GPU check scripts), `__graft_entry__.smoke()` and `bench.py`'s baseline leg (`cpu_baseline`, which also
+runs these torch modules in eager fp32 on the GPU as the checker of the full population, and `--impl reference`) may import this
+module; the product package and the `tools_*` scripts never do (the product fails loudly without its CUDA library).
 
 Pinning (see tests/golden/make_golden.py, tests/test_oracle_golden.py):
   * cell statistics are pinned by the reference's own golden vector

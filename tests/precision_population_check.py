@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Full-population precision check on the bench scene: probabilities of every cell from the f16f8 and bf16x3 engines and
 from the reference modules in eager fp32, all against the same modules in fp64 (ground truth).
-usage: tools_precision_population.py [size] [panel]"""
-import json, sys, torch, numpy as np
-sys.path.insert(0, ".")
+usage: python tests/precision_population_check.py [size] [panel]   (a GPU script like tests/multi_gpu_check.py, not collected by pytest)"""
+import json, os, sys, torch, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multiplexed_image_annotator_b200 import engine, ops, synth, weights
 from multiplexed_image_annotator_b200.cell_type_annotation.model import merge_on_device
 from oracle import ribca_oracle as orc

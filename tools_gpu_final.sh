@@ -11,5 +11,5 @@ r = json.load(open("gpurun_out/final_bench_ref.json")); print("ref", r["value"],
 d = json.load(open("gpurun_out/final_bench.json"))
 print("b200", d["value"], d["e2e"]["value"], d["ms_per_step"], d["gpu_launches"], d["clocks"])
 print(d["roofline"]["frac"], d["roofline"]["issued_frac"], d["roofline"]["traffic"])
-print(d["parity_sample"]); print(d["reference_gpu_path"]["full_population_parity"], d["reference_gpu_path"]["stage4_ms"])
+print(d["parity_sample"]); print(d["parity_population"], d["cpu_baseline"]["reference_gpu_path"]["stage4_ms"])
 PY
