@@ -1,10 +1,10 @@
-"""CPU emulation of the tensor-core operand formats on the whole vit_l (research script, not part of the product or the tests).
+"""CPU emulation of the tensor-core operand formats on the whole vit_l (research script like tests/multi_gpu_check.py: not collected by pytest, not part of the product).
 
 Quantises the operands of every Linear / attention matmul as the kernels would (bf16x1, fp16x1, bf16x3, fp16 + split weights,
 fp16 + split activations, f16f8 = fp16 main pass + e4m3 correction pairs) and reports max |dprob| against plain fp32 on the cells
 of a synthetic scene; `fold:<mode>` additionally applies LayerNorm algebraically in the consumer GEMM's epilogue
 (LN(x) W^T = rstd (x (g*W)^T - mean c1) + c2 on RAW x operands), the formulation proposed in DESIGN.md "what comes next".
-    python tools_research/precision_emulation.py 768 immune_full "bf16x3,bf16x1,fp16x1,f16f8:8/bf16x3,fold:f16f8:8/bf16x3"
+    python tests/precision_emulation_check.py 768 immune_full "bf16x3,bf16x1,fp16x1,f16f8:8/bf16x3,fold:f16f8:8/bf16x3"
 Results behind DESIGN.md section 4 (1849 cells): bf16x3 5.6e-5, bf16x1 3.4e-2, fp16x1 3.7e-3, f16f8 1.3e-4, folded f16f8 1.2e-4.
 """
 import sys, os, time, math
