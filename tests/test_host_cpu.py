@@ -328,3 +328,30 @@ def test_ome_channel_names(tmp_path):
     assert bio.ome_channel_names(path) == ["DAPI", "CD45", "PanCK"]
     _write_tiff(path, [np.zeros((8, 8), np.uint16)], description="not xml")
     assert bio.ome_channel_names(path) is None
+
+
+def test_tiff_reader_property_random_layouts(tmp_path):
+    """Random page counts / shapes / sample types / byte orders / strip vs tile layouts / classic vs Big: write with the test
+    writer, read back bit-exactly; and a page the reader cannot take raw (here: a corrupted offset table) raises instead of
+    returning garbage."""
+    from hypothesis import given, settings, strategies as st
+    from multiplexed_image_annotator_b200 import io as bio
+    path = str(tmp_path / "h.tif")
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 4), st.integers(1, 40), st.integers(1, 50), st.sampled_from(["u1", "u2", "i2", "u4", "i4", "f4"]),
+           st.booleans(), st.sampled_from(["<", ">"]), st.sampled_from([None, 16, 32]), st.integers(0, 2 ** 31))
+    def check(pages, h, w, dt, big, bo, tile, seed):
+        rng = np.random.default_rng(seed)
+        stack = (rng.random((pages, h, w)) * 200).astype(np.dtype(dt))
+        _write_tiff(path, list(stack), big=big, bo=bo, tile=tile)
+        got = bio.read_tiff_stack(path, pin=False)
+        assert got.dtype == np.dtype(dt) and got.shape == stack.shape and np.array_equal(got, stack)
+
+    check()
+    # truncated file: the strip read must fail loudly
+    _write_tiff(path, [np.arange(200, dtype=np.uint16).reshape(10, 20)])
+    blob = open(path, "rb").read()
+    open(path, "wb").write(blob[:8] + blob[8:60])          # header + part of the first strip, IFD gone
+    with pytest.raises((ValueError, IOError, Exception)):
+        bio.read_tiff_stack(path, pin=False)
