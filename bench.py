@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of RIBCA's per-cell annotation hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size S] [--workload c2|c3]
 
-A "step" is one pass of the whole hot path (normalise -> cell statistics -> patches -> vit_l ->
-merge/threshold/count) over one synthetic 15-marker S x S image (default S = 4096, BASELINE.json
-configs[1], ~51.8 k cells, immune_full panel).  Metric: cells/sec.
-  value  inputs already resident in HBM when the timed region starts
-  e2e    the same through HotPath.run with HOST (pinned) image + mask: H2D copies and the D2H read of
-         labels / confidences / counts are inside the timed region
-With N > 1 (torchrun, one rank per GPU) every rank annotates its own image (the batch-CSV sharding of
-configs[4]; weak scaling) and the per-type counts are all-reduced over NCCL; value = cells of all ranks
-/ max-over-ranks device time.
---impl reference times the CPU oracle (the reference's algorithm on the host cores, torch threads =
-all cores) on a bounded crop of the same workload.
+A "step" is one pass of the whole hot path (normalise -> cell statistics -> patches -> vit_l -> merge / threshold /
+count, with the margin-guarded re-evaluation that makes the labels exact) over one synthetic 15-marker S x S image
+(default S = 4096, BASELINE.json configs[1], ~51.8 k cells, immune_full panel).  Metric: cells/sec.
+  value          inputs already resident in HBM when the timed region starts
+  e2e            the same through HotPath.run with HOST (pinned) image + mask: H2D copies and the D2H read of
+                 labels / confidences / counts are inside the timed region
+  e2e_annotator  (N = 1) the reference-shaped API: Annotator(...).preprocess() + predict() from the .npy files on disk
+With N > 1 (torchrun, one rank per GPU) the headline `value` is WEAK scaling: every rank annotates its own image and the
+per-type counts are all-reduced over NCCL.  Two more records ride on the same line:
+  strong   BASELINE configs[3] shape: ONE image (default 8192^2, ~207 k cells) in pinned host memory, cells sharded by
+           contiguous range over the ranks, stage 1 split by channel, one gather of labels / confidences; per-phase
+           device times and the SHA-256 of all labels + confidences (identical at every N)
+  batch    BASELINE configs[4]: 64 images of 2048^2 in four marker-file groups (full / structure / nerve /
+           structure + nerve), images round-robin over the ranks through HotPath.run_batch
+--impl reference times the CPU oracle (the reference's algorithm on the host cores, torch threads = all cores) on a
+bounded crop of the same workload; the in-line `cpu_baseline` of the b200 arm uses the same crop rule.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,6 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = "cells/sec end-to-end (RIBCA per-cell annotation hot path)"
 FLOP_PER_CELL = {"immune_full": 9.96e9, "immune_extended": 4.48e9, "immune_base": 2.55e9, "structure": 2.55e9,
                  "nerve_cell": 0.67e9}            # SURVEY 2b, algorithmic (no padding, no split passes)
+C3_INDEX, C3_PRESENT = [0, 1, 2, 3, 4, -1, 5], [0, 1, 2, 3, 4, 6]     # CD45,CD20,CD4,CD8,DAPI,CD3 -> immune_base, CD11c missing
 
 
 def parse():
@@ -49,6 +56,11 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2: 15-marker full panel -> vit_l (headline, BASELINE configs[1]); c3: 6-marker basic panel with "
                          "CD11c missing -> MAE imputer + vit_s (configs[2], secondary)")
+    ap.add_argument("--strong-size", type=int, default=8192, help="edge of the ONE image of the strong-scaling record (0 = skip)")
+    ap.add_argument("--strong-steps", type=int, default=2)
+    ap.add_argument("--batch-images", type=int, default=64, help="images of the batch-CSV record (0 = skip)")
+    ap.add_argument("--batch-size", type=int, default=2048)
+    ap.add_argument("--no-annotator", action="store_true", help="skip the e2e_annotator leg")
     return ap.parse_args()
 
 
@@ -96,69 +108,110 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_scene(size, seed, device, channels=15):
+def make_scene(size, seed, device, channels=15, grid=18):
     from multiplexed_image_annotator_b200 import synth
-    mask = synth.synth_mask(size, size, grid=18, seed=seed, device=device)
+    mask = synth.synth_mask(size, size, grid=grid, seed=seed, device=device)
     img = synth.synth_image(mask, channels, seed=seed)
     return img, mask
 
 
-def cpu_oracle_rate(img_u16, mask_i32, sd, edge, threads):
+def sample_edge(steps, warmup):
+    """Edge of the CPU sample crop: the SAME rule for `--impl reference` and the in-line cpu_baseline, sized so that
+    (steps + warmup) oracle passes end within a few minutes (~26 cells/s/8 cores probed)."""
+    total = steps + warmup
+    return 512 if total <= 12 else (384 if total <= 24 else 256)
+
+
+def cpu_oracle_rate(img_u16, mask_i32, sd, edge, threads, panel="immune_full", index=None, mae_sd=None, present=None):
     """cells/sec of the reference algorithm (oracle) on a crop of the workload, host cores only; the stages are the calls of
     orc.annotate_image, timed one by one (per-stage CPU rates next to the total)."""
     from oracle import ribca_oracle as orc
     torch.set_num_threads(threads)
     crop_i = np.ascontiguousarray(img_u16[:, :edge, :edge])
     crop_m = np.ascontiguousarray(mask_i32[:edge, :edge])
-    model = orc.make_vit("immune_full")
+    model = orc.make_vit(panel)
     model.load_state_dict(sd)
-    index = list(range(15))
+    index = list(range(crop_i.shape[0])) if index is None else index
+    mae = None
+    if mae_sd is not None:
+        mae = orc.make_mae(panel)
+        mae.load_state_dict(mae_sd)
     t = [time.perf_counter()]
     img = orc.normalize(crop_i, 0.3, 99.8); t.append(time.perf_counter())
     stats = orc.cell_stats(crop_m); t.append(time.perf_counter())
     pt, inten, wins = orc.build_patches(img, crop_m, index, stats, 30); t.append(time.perf_counter())
+    if mae is not None:
+        pt = orc.impute(mae, pt, present)
+    t_imp = time.perf_counter()
     probs = orc.vit_probs(model, pt, 128); t.append(time.perf_counter())
-    labels, conf = orc.merge_by_voting({"immune_full": probs}, 0.3, None); t.append(time.perf_counter())
+    labels, conf = orc.merge_by_voting({panel: probs}, 0.3, None); t.append(time.perf_counter())
     dt = t[-1] - t[0]
     n = len(labels)
     mpx_ch = crop_i.shape[0] * edge * edge / 1e6
     stages = {"1_normalize_ms_per_Mpx_channel": 1e3 * (t[1] - t[0]) / mpx_ch, "2_cell_stats_us_per_pixel": 1e6 * (t[2] - t[1]) / (edge * edge),
-              "3_build_patches_ms_per_cell": 1e3 * (t[3] - t[2]) / max(n, 1), "4_vit_l_ms_per_cell": 1e3 * (t[4] - t[3]) / max(n, 1),
+              "3_build_patches_ms_per_cell": 1e3 * (t[3] - t[2]) / max(n, 1), "4_networks_ms_per_cell": 1e3 * (t[4] - t[3]) / max(n, 1),
+              "4a_of_which_imputer_ms_per_cell": 1e3 * (t_imp - t[3]) / max(n, 1),
               "5_merge_us_per_cell": 1e6 * (t[5] - t[4]) / max(n, 1)}
-    # extrapolation to the full workload (15 x 4096^2, n_full cells): labelled as such
-    res = {"labels": labels, "confidence": conf, "probs": {"immune_full": probs}, "stages": stages}
+    res = {"labels": labels, "confidence": conf, "probs": {panel: probs}, "stages": stages}
     return n / dt, res, dt
+
+
+def workload_models(args, dev=None):
+    """(panel, channel index, n_markers, vit state, mae state or None) of the selected workload."""
+    from multiplexed_image_annotator_b200 import weights
+    if args.workload == "c2":
+        return "immune_full", list(range(15)), 15, weights.random_vit_state("immune_full", seed=7), None
+    return "immune_base", C3_INDEX, 6, weights.random_vit_state("immune_base", seed=7), weights.random_mae_state("immune_base", seed=7)
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from multiplexed_image_annotator_b200 import synth, weights
+    from multiplexed_image_annotator_b200 import synth
     threads = os.cpu_count() or 1
-    # bounded sample: ~25 s of work per step on 8 cores at the probed ~26 cells/s (BASELINE.md 3)
     total = args.steps + args.warmup
-    edge = 512 if total <= 4 else (384 if total <= 8 else 256)
-    img, mask = make_scene(max(edge, 512), 2, "cpu")
+    edge = sample_edge(args.steps, args.warmup)
+    panel, index, n_markers, sd, mae_sd = workload_models(args)
+    img, mask = make_scene(max(edge, 512), 2, "cpu", n_markers)
     img_u16, mask_i32 = synth.to_uint16(img), mask.numpy()
-    sd = weights.random_vit_state("immune_full", seed=7)
     rates, cells = [], 0
     for s in range(total):
-        r, res, dt = cpu_oracle_rate(img_u16, mask_i32, sd, edge, threads)
+        r, res, dt = cpu_oracle_rate(img_u16, mask_i32, sd, edge, threads, panel, index, mae_sd, C3_PRESENT if mae_sd else None)
         cells = len(res["labels"])
         if s >= args.warmup:
             rates.append((cells, dt))
     n = sum(c for c, _ in rates)
     t = sum(d for _, d in rates)
     val = n / t
-    sample = f"{edge}x{edge} crop of the 15-marker scene, {cells} cells per step, oracle (numpy/scipy/torch fp32) preprocess+predict"
+    what = "immune_full panel / vit_l" if args.workload == "c2" else "immune_base panel, CD11c imputed by the MAE, vit_s"
+    sample = f"{edge}x{edge} crop of the {n_markers}-marker scene, {cells} cells per step, oracle (numpy/scipy/torch fp32) preprocess+predict"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * t / max(len(rates), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2 sample: synthetic 15-marker image, immune_full panel / vit_l, {sample}"},
+        "config": {"workload": f"{args.workload.upper()} sample: synthetic {n_markers}-marker image, {what}, {sample}"},
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def decision_report(ref_probs, got_probs, lab_ref, lab_got, margin_ref):
+    """Label parity with its sensitivity (SURVEY 8d 'always report'): final-label agreement, pre-threshold argmax agreement,
+    how many cells sit within 1e-3 / 1e-4 of a decision boundary of the checker, and the checker's top-2 gap histogram."""
+    top = torch.topk(ref_probs, 2, dim=1).values
+    gap = (top[:, 0] - top[:, 1]).double().cpu().numpy()
+    edges = [0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1.0000001]
+    hist = np.histogram(gap, bins=edges)[0].tolist()
+    n = int(lab_ref.numel())
+    differ = int((lab_ref != lab_got).sum().item())
+    am = int((ref_probs.argmax(1) != got_probs.argmax(1)).sum().item())
+    m = margin_ref.double().cpu().numpy()
+    return {"cells": n, "labels_differ": differ, "label_agreement": 1.0 - differ / max(n, 1),
+            "argmax_differ_pre_threshold": am, "argmax_agreement_pre_threshold": 1.0 - am / max(n, 1),
+            "max_abs_dprob": float((ref_probs - got_probs).abs().max().item()),
+            "cells_within_1e-3_of_a_decision_boundary": int((m < 1e-3).sum()), "cells_within_1e-4_of_a_decision_boundary": int((m < 1e-4).sum()),
+            "cells_labelled_others_by_threshold": int((lab_ref == 17).sum().item()),
+            "top2_gap_histogram": {"bin_edges": edges[:-1] + [1.0], "cells": hist}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -167,8 +220,8 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
     import torch.distributed as dist
-    from multiplexed_image_annotator_b200 import _lib, engine, ops, synth, weights
-    from multiplexed_image_annotator_b200.cell_type_annotation.model import ALL_TYPES
+    from multiplexed_image_annotator_b200 import _lib, engine, exact, ops, synth, weights
+    from multiplexed_image_annotator_b200.cell_type_annotation.model import ALL_TYPES, merge_on_device
     from multiplexed_image_annotator_b200.pipeline import HotPath
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,25 +247,33 @@ def main():
             os.close(saved_fd)
     L = _lib.lib()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- workload: one synthetic scene per rank, host copy in pinned memory ----------------------------
     S = args.size
-    n_markers = 15 if args.workload == "c2" else 6
+    panel, index, n_markers, sd, mae_sd = workload_models(args)
     img_i32, mask_d = make_scene(S, 2 + rank, dev, n_markers)
     img_host = torch.from_numpy(synth.to_uint16(img_i32)).pin_memory()
     mask_host = mask_d.cpu().pin_memory()
     del img_i32
     img_dev = img_host.to(dev)
-    if args.workload == "c2":
-        panel, index, imputers = "immune_full", list(range(15)), {}
-    else:       # markers CD45,CD20,CD4,CD8,DAPI,CD3 -> immune_base index [0,1,2,3,4,-1,5], strict=False, infer=True
-        panel, index = "immune_base", [0, 1, 2, 3, 4, -1, 5]
-        mae = engine.MaeEngine(panel, weights.random_mae_state(panel, seed=7), dev, precision=args.precision)
-        imputers = {panel: (mae, [0, 1, 2, 3, 4, 6])}
-        args.no_cpu_baseline = True
-    sd = weights.random_vit_state(panel, seed=7)
+    imputers = {}
+    if mae_sd is not None:       # markers CD45,CD20,CD4,CD8,DAPI,CD3 -> immune_base index [0,1,2,3,4,-1,5], strict=False, infer=True
+        mae = engine.MaeEngine(panel, mae_sd, dev, precision=args.precision)
+        imputers = {panel: (mae, C3_PRESENT)}
     eng = engine.VitEngine(panel, sd, dev, precision=args.precision, max_cells_per_call=args.chunk)
     hp = HotPath({panel: index}, {panel: eng}, imputers, chunk_cells=args.chunk, device=dev, shard_cells=False)
-    # head calibration: spread the label histogram of the random-init classifier
+    # head calibration: spread the label histogram of the random-init classifier.  Rank 0's statistics serve
+    # every rank, so that all ranks hold the SAME model (the strong-scaling record shards one image over them).
     warm = hp.run(img_dev, mask_d, to_host=False, keep_probs=True)
     n_cells = warm.n_cells
     norm = ops.normalize(img_dev, 0.3, 99.8)
@@ -220,14 +281,12 @@ def main():
     if imputers:
         imputers[panel][0].impute(p256, imputers[panel][1])
     _, logits = eng.forward(p256, return_logits=True)
-    sd_cal = weights.calibrate_head(sd, logits.mean(0).cpu().numpy(), 20.0)
+    mean_logits = logits.mean(0)
+    if world > 1:
+        dist.broadcast(mean_logits, src=0)
+    sd_cal = weights.calibrate_head(sd, mean_logits.cpu().numpy(), 20.0)
     eng.set_head(sd_cal["head.weight"], sd_cal["head.bias"])
     del norm, p256, warm
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -240,10 +299,7 @@ def main():
             out = fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out, ops.launch_count() - l0
+        return max_over_ranks(e0.elapsed_time(e1)), out, ops.launch_count() - l0
 
     def step_resident():
         r = hp.run(img_dev, mask_d, to_host=False)
@@ -261,7 +317,7 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res, res, launches = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, res_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 3))
+    ms_e2e, res_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else {}
 
     cells_all = torch.tensor([n_cells], device=dev, dtype=torch.float64)
@@ -270,12 +326,14 @@ def main():
     total_cells = float(cells_all.item())
     value = total_cells * args.steps / (ms_res / 1000)
     e2e_value = total_cells * args.steps / (ms_e2e / 1000)
+    refine = res.refine.as_dict()
+    refine["share_of_step"] = sum(refine["level_ms"]) / (ms_res / args.steps)
 
     # ---- roofline of the dominant kernel, measured live with CUDA events around every launch -----------
     import ctypes as C
     L.ribca_profile_begin()
     hp.run(img_dev, mask_d, to_host=False)
-    nc = 7
+    nc = 8
     ms = (C.c_double * nc)(); ln = (C.c_longlong * nc)(); wk = (C.c_double * nc)()
     _lib.check(L.ribca_profile_end(ms, ln, wk, nc), "ribca_profile_end")
     pk, pk_src = peaks()
@@ -297,6 +355,8 @@ def main():
                 "launches_per_step": int(ln[0]), "avg_launch_ms": ms[0] / max(ln[0], 1), "kernel_ms_per_step": ms[0],
                 "algorithmic_flop_per_step": wk[0], "tensor_passes": passes, "issued_frac": passes * gemm_tf / peak_tf,
                 "share_of_step": ms[0] / (ms_res / args.steps),
+                "note": "GEMM launches of the profiled step include the bf16x3 re-evaluation of the boundary cells (3 passes); "
+                        "issued_frac counts them as the default precision's passes",
                 "other_kernels": {
                     "attention_kernel": {"ms_per_step": ms[1], "launches": int(ln[1]), "tflops_fp32": wk[1] / (ms[1] / 1000) / 1e12 if ms[1] > 0 else 0},
                     "build_patches_kernel": {"ms_per_step": ms[2], "launches": int(ln[2]), "achieved_gbs": wk[2] / (ms[2] / 1000) / 1e9 if ms[2] > 0 else 0,
@@ -316,25 +376,29 @@ def main():
                            "issued_frac": passes * gemm_tf / peak_tf},
         "4_attention_tc": {"ms_per_step": ms[1], "launches": int(ln[1]), "algorithmic_tflops": wk[1] / (ms[1] / 1000) / 1e12 if ms[1] > 0 else 0.0},
         "4_layernorm": hbm_stage(5),
+        "4_sgemm_fp32_reevaluation": {"ms_per_step": ms[7], "launches": int(ln[7]), "tflops_fp32": wk[7] / (ms[7] / 1000) / 1e12 if ms[7] > 0 else 0.0},
         "5_merge": hbm_stage(6),
     }
 
     # ---- CPU baseline + label agreement on a bounded sample (rank 0, N = 1 only) -------------------------
     cpu_baseline, agreement = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ribca_oracle as orc                         # checker / baseline only
         threads = os.cpu_count() or 1
-        edge = min(768, S)                       # ~1850 cells, ~15 s of host work
+        edge = min(sample_edge(args.steps, args.warmup), S)          # the crop rule of --impl reference
         img_u16 = img_host.numpy()
-        rate, ores, dt = cpu_oracle_rate(img_u16, mask_host.numpy(), sd_cal, edge, threads)
+        rate, ores, dt = cpu_oracle_rate(img_u16, mask_host.numpy(), sd_cal, edge, threads, panel, index, mae_sd, C3_PRESENT if mae_sd else None)
         crop = hp.run(np.ascontiguousarray(img_u16[:, :edge, :edge]), np.ascontiguousarray(mask_host.numpy()[:edge, :edge]),
                       to_host=True, keep_probs=True)
-        same = sum(a == b for a, b in zip(crop.names(), ores["labels"]))
-        dprob = float(np.abs(crop.probs[panel].cpu().numpy() - ores["probs"][panel]).max())
-        agreement = {"cells": len(ores["labels"]), "label_agreement": same / len(ores["labels"]), "max_abs_dprob": dprob,
-                     "labels_present": sorted(set(ores["labels"]))}
+        oprobs = torch.from_numpy(ores["probs"][panel]).to(dev)
+        olab, _, _, omargin = merge_on_device({panel: oprobs}, 0.3, None, want_margin=True)
+        agreement = decision_report(oprobs, crop.probs[panel], olab, crop.label.to(dev), omargin)
+        agreement["labels_present"] = sorted(set(ores["labels"]))
+        agreement["names_equal"] = crop.names() == list(ores["labels"])
+        agreement["reevaluation"] = crop.refine.as_dict()
         st = ores["stages"]
-        full_s = (st["1_normalize_ms_per_Mpx_channel"] * 15 * S * S / 1e6 + st["2_cell_stats_us_per_pixel"] * S * S / 1e3
-                  + (st["3_build_patches_ms_per_cell"] + st["4_vit_l_ms_per_cell"]) * n_cells + st["5_merge_us_per_cell"] * n_cells / 1e3) / 1e3
+        full_s = (st["1_normalize_ms_per_Mpx_channel"] * n_markers * S * S / 1e6 + st["2_cell_stats_us_per_pixel"] * S * S / 1e3
+                  + (st["3_build_patches_ms_per_cell"] + st["4_networks_ms_per_cell"]) * n_cells + st["5_merge_us_per_cell"] * n_cells / 1e3) / 1e3
         cpu_baseline = {"value": rate, "unit": "cells/s", "cores": threads, "kind": "port",
                         "sample": f"{edge}x{edge} crop of the same scene, {len(ores['labels'])} cells, {dt:.1f} s, "
                                   "oracle (numpy/scipy/torch fp32) preprocess+predict",
@@ -344,9 +408,7 @@ def main():
     #      baseline") = the oracle's torch modules in eager fp32 on this GPU, bs = 128 slices as cta/model.py:397-406, which also
     #      serves as the checker of the step's labels over the whole population
     ref_gpu = None
-    if cpu_baseline is not None and args.workload == "c2":
-        from oracle import ribca_oracle as orc                         # checker / baseline only
-        from multiplexed_image_annotator_b200.cell_type_annotation.model import merge_on_device
+    if cpu_baseline is not None:
         # strict fp32 like the reference's CPU path: cuDNN would otherwise run the patch-embedding conv in TF32, which alone
         # costs the stock GPU path ~1.5e-3 of probability (profiles/precision_population_r01.json)
         torch.backends.cudnn.allow_tf32 = False
@@ -361,6 +423,8 @@ def main():
         with torch.no_grad():
             for a in range(0, n_cells, 8192):
                 (pt,), _, _ = ops.build_patches(norm, mask_d, mn, full.cells, [index], a, min(8192, n_cells - a))
+                if imputers:       # the checker classifies the SAME imputed inputs (the imputer has its own parity tests)
+                    imputers[panel][0].impute(pt, imputers[panel][1], precision="bf16x3")
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -370,43 +434,204 @@ def main():
                 t_ref += e0.elapsed_time(e1)
                 ref_probs.append(torch.cat(outs))
         ref_probs = torch.cat(ref_probs)
-        lab_ref, _, _ = merge_on_device({panel: ref_probs}, 0.3, None)
-        differ = int((lab_ref != full.label).sum().item())
-        ref_gpu = {"what": "oracle vit_l (plain torch.nn, eager fp32, TF32 off for matmul and cuDNN) forward + softmax on this GPU in bs = 128 slices, "
+        lab_ref, _, _, margin_ref = merge_on_device({panel: ref_probs}, 0.3, None, want_margin=True)
+        pop = decision_report(ref_probs, full.probs[panel], lab_ref, full.label, margin_ref)
+        pop["checker"] = "oracle torch modules, eager strict fp32 on this GPU, all cells of the step"
+        pop["reevaluation"] = full.refine.as_dict()
+        ref_gpu = {"what": "oracle classifier (plain torch.nn, eager fp32, TF32 off for matmul and cuDNN) forward + softmax on this GPU in bs = 128 slices, "
                            "patches resident in HBM (no per-batch H2D / D2H, which the reference also pays)",
                    "cells": n_cells, "stage4_ms": t_ref, "stage4_cells_per_s": n_cells / (t_ref / 1000),
-                   "b200_stage4_ms": ms[0] + ms[1] + ms[5],
-                   "full_population_parity": {"cells": n_cells, "labels_differ": differ, "label_agreement": 1.0 - differ / n_cells,
-                                              "max_abs_dprob": float((ref_probs - full.probs[panel]).abs().max().item())}}
+                   "b200_stage4_ms": ms[0] + ms[1] + ms[5], "full_population_parity": pop}
         del ref_model, ref_probs, norm, full
         cpu_baseline["reference_gpu_path"] = {k: v for k, v in ref_gpu.items() if k != "full_population_parity"}
 
+    # ---- the reference-shaped API end to end: Annotator(...).preprocess() + predict() from files on disk (N = 1) ---------
+    e2e_annotator = None
+    if rank == 0 and world == 1 and not args.no_annotator:
+        e2e_annotator = annotator_leg(args, img_host, mask_host, panel, sd_cal, mae_sd, n_cells, res_e2e)
+
+    del img_dev
+    torch.cuda.empty_cache()
+    strong = strong_record(args, dev, world, rank, eng, hp, barrier, max_over_ranks) if args.strong_size and args.workload == "c2" else None
+    batch = batch_record(args, dev, world, rank, eng, barrier, max_over_ranks) if args.batch_images and args.workload == "c2" else None
+
     if rank == 0:
         hist = np.bincount(res_e2e.label.numpy(), minlength=18)
+        what = (f"C2: synthetic 15-marker {S}x{S} uint16 image + int32 mask per GPU, {n_cells} cells, "
+                f"immune_full panel -> vit_l (random-init, calibrated head), blur 0.3, amax 99.8, confidence 0.3"
+                if args.workload == "c2" else
+                f"C3: synthetic 6-marker {S}x{S} image (basic panel, CD11c missing), {n_cells} cells, strict=False infer=True "
+                f"-> MAE imputer (L=7, keep 6) + vit_s, blur 0.3, amax 99.8, confidence 0.3")
         out = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": f"{args.precision} tensor-core passes, fp32 accumulate (stages 1-3 f32/f64 exact order)",
+            "dtype": f"{args.precision} tensor-core passes, fp32 accumulate (stages 1-3 f32/f64 exact order); boundary cells re-evaluated in bf16x3 / fp32",
             "data": "synthetic",
-            "config": {"workload": (f"C2: synthetic 15-marker {S}x{S} uint16 image + int32 mask per GPU, {n_cells} cells, "
-                                    f"immune_full panel -> vit_l (random-init, calibrated head), blur 0.3, amax 99.8, confidence 0.3")
-                       if args.workload == "c2" else
-                       (f"C3: synthetic 6-marker {S}x{S} image (basic panel, CD11c missing), {n_cells} cells, strict=False infer=True "
-                        f"-> MAE imputer (L=7, keep 6) + vit_s, blur 0.3, amax 99.8, confidence 0.3"),
+            "config": {"workload": what + f"; CPU arms run a {sample_edge(args.steps, args.warmup)}^2 crop of the same scene",
                        "cells_per_gpu": n_cells, "chunk_cells": args.chunk, "precision": args.precision,
+                       "exact_labels": {"levels": hp.exact_labels, "eps": [exact.EPS1, exact.EPS2]},
                        "l2": f"inputs ({img_host.numel() * 2 / 1e6:.0f} MB image + {mask_host.numel() * 4 / 1e6:.0f} MB mask) exceed the 126 MB L2",
                        "parallelism": f"{world} x (one image per GPU), all-reduce of 18 counts"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(img_host.numel() * 2 + mask_host.numel() * 4),
                     "d2h_bytes_per_step": int(n_cells * 5 + 18 * 8)},
+            "e2e_annotator": e2e_annotator,
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline, "parity_sample": agreement,
+            "clocks": clocks, "roofline": roofline, "stages": stages, "reevaluation": refine,
+            "cpu_baseline": cpu_baseline, "parity_sample": agreement,
             "parity_population": None if ref_gpu is None else ref_gpu["full_population_parity"],
             "label_histogram": {ALL_TYPES[k]: int(v) for k, v in enumerate(hist) if v},
+            "strong": strong, "batch": batch,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def annotator_leg(args, img_host, mask_host, panel, sd_cal, mae_sd, n_cells, res_e2e):
+    """Annotator(...).preprocess() + predict() (what main.py:19-20 / gui_api.py:23-24 call) on the bench scene stored as
+    .npy files: wall clock around the two calls, CUDA-synchronised, file read and Python result assembly included."""
+    from multiplexed_image_annotator_b200 import synth
+    from multiplexed_image_annotator_b200.cell_type_annotation import markerImputer as bimp
+    from multiplexed_image_annotator_b200.cell_type_annotation import model as bmodel
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        os.chdir(tmp)
+        try:
+            np.save("img.npy", img_host.numpy())
+            np.save("mask.npy", mask_host.numpy())
+            markers = synth.FULL_PANEL_MARKERS if args.workload == "c2" else ["CD45", "CD20", "CD4", "CD8", "DAPI", "CD3"]
+            synth.write_marker_file("markers.txt", markers)
+            with open("images.csv", "w") as f:
+                f.write("image_path,mask_path\nimg.npy,mask.npy\n")
+            bmodel.register_state(panel, sd_cal)
+            if mae_sd is not None:
+                bimp.register_state(panel, mae_sd)
+            times, ann = [], None
+            for _ in range(2):                                    # first pass warms the allocator and the page cache
+                del ann
+                ann = bmodel.Annotator("markers.txt", "images.csv", "cuda", "./", "bench", args.workload == "c2", True, -1, True,
+                                       0.3, 99.8, 0.3, 30, None, n_jobs=0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ann.preprocess()
+                t1 = time.perf_counter()
+                ann.predict(128)
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                times.append((t1 - t0, t2 - t1))
+            same = bool(np.array_equal(ann.labels_index[0], res_e2e.label.numpy()))
+            pre_s, pred_s = times[-1]
+            return {"value": n_cells / (pre_s + pred_s), "unit": "cells/s", "preprocess_s": pre_s, "predict_s": pred_s,
+                    "what": "Annotator(markers.txt, images.csv, 'cuda', ...).preprocess() + .predict(128): .npy image + mask read from "
+                            "disk (tmpfs), stages 1-5, labels / confidences / probabilities / intensities back on the host as the "
+                            "reference's attributes; wall clock, second of two runs",
+                    "labels_equal_hot_path": same, "file_bytes": int(img_host.numel() * 2 + mask_host.numel() * 4)}
+        finally:
+            os.chdir(cwd)
+
+
+def strong_record(args, dev, world, rank, eng, hp_weak, barrier, max_over_ranks):
+    """BASELINE configs[3] shape on N GPUs: ONE image in pinned host memory, sharded by cell range."""
+    import torch.distributed as dist
+    from multiplexed_image_annotator_b200 import synth
+    from multiplexed_image_annotator_b200.pipeline import HotPath
+    S = args.strong_size
+    img_i32, mask_d = make_scene(S, 4, dev, 15, grid=18)
+    img_host = torch.from_numpy(synth.to_uint16(img_i32)).pin_memory()          # the same bytes on every rank = one file
+    mask_host = mask_d.cpu().pin_memory()
+    del img_i32, mask_d
+    torch.cuda.empty_cache()
+    hp = HotPath(hp_weak.panels, hp_weak.models, chunk_cells=args.chunk, device=dev, shard_cells=True)
+    hp.run(img_host, mask_host, to_host=True)                                   # warm-up (allocator, NCCL channels)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.strong_steps):
+        res = hp.run(img_host, mask_host, to_host=True, time_phases=True)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.strong_steps
+    phases = res.phases.ms()
+    names = sorted(phases)
+    t = torch.tensor([phases[k] for k in names], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = res.refine
+    rv = torch.tensor(st.reevaluated + st.relabelled, device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(rv)
+    digest = hashlib.sha256(res.label.numpy().tobytes() + res.confidence.numpy().tobytes()).hexdigest()
+    n = res.n_cells
+    c = img_host.shape[0]
+    own = len(range(rank, c, world)) if world > 1 else c
+    return {"what": f"ONE synthetic 15-marker {S}x{S} uint16 image + int32 mask in pinned host memory, {n} cells, cells sharded by "
+                    f"contiguous range over {world} rank(s); stage 1 split by channel with NCCL broadcasts of the normalised planes; "
+                    "one all-gather of labels / confidences + all-reduce of counts; results on the host of every rank",
+            "scaling": "strong", "n_gpus": world, "cells": n, "steps": args.strong_steps, "ms_per_step": ms,
+            "value": n / (ms / 1000), "unit": "cells/s",
+            "phases_ms_max_over_ranks": {k: float(v) for k, v in zip(names, t.tolist())},
+            "h2d_bytes_per_rank": int(own * img_host[0].numel() * 2 + mask_host.numel() * 4),
+            "nccl_bytes": {"plane_broadcasts": int(c * img_host[0].numel() * 4) if world > 1 else 0,
+                           "gather": int(n * 5 + 18 * 8) if world > 1 else 0},
+            "reevaluated_cells_level1_level2": rv.tolist()[:2], "relabelled_level1_level2": rv.tolist()[2:],
+            "labels_confidences_sha256": digest, "counts": res.counts.tolist(),
+            "max_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+
+
+def batch_record(args, dev, world, rank, eng_full, barrier, max_over_ranks):
+    """BASELINE configs[4]: a batch-processing CSV of images in four marker-file groups (one marker file per CSV is the
+    reference's constraint), images round-robin over the ranks (HotPath.run_batch)."""
+    from multiplexed_image_annotator_b200 import engine, synth, weights
+    from multiplexed_image_annotator_b200.parallel import image_owner
+    from multiplexed_image_annotator_b200.pipeline import HotPath
+    S, per_group = args.batch_size, max(args.batch_images // 4, 1)
+    struct = engine.VitEngine("structure", weights.random_vit_state("structure", seed=8), dev, max_cells_per_call=args.chunk)
+    nerve = engine.VitEngine("nerve_cell", weights.random_vit_state("nerve_cell", seed=9), dev, max_cells_per_call=args.chunk)
+    groups = [   # (name, markers, panels -> channel index, models)
+        ("full15_branch5", 15, {"immune_full": list(range(15))}, {"immune_full": eng_full}),
+        ("structure7_branch6", 7, {"structure": list(range(7))}, {"structure": struct}),
+        ("nerve3_branch7", 3, {"nerve_cell": [0, 1, 2]}, {"nerve_cell": nerve}),
+        ("structure_plus_gfap_branch3", 8, {"structure": list(range(7)), "nerve_cell": [0, 6, 7]}, {"structure": struct, "nerve_cell": nerve}),
+    ]
+    work = []
+    h2d = 0
+    for g, (name, ch, panels, models) in enumerate(groups):
+        items = []
+        for i in range(per_group):
+            if image_owner(i, world) != rank:
+                items.append(None)
+                continue
+            img, m = make_scene(S, 100 + 16 * g + i, dev, ch)
+            items.append((torch.from_numpy(synth.to_uint16(img)).pin_memory(), m.cpu().pin_memory()))
+            h2d += items[-1][0].numel() * 2 + items[-1][1].numel() * 4
+        work.append((name, HotPath(panels, models, chunk_cells=args.chunk, device=dev), items))
+    torch.cuda.empty_cache()
+
+    def one_pass():
+        return [(name, hp.run_batch(items, to_host=True)) for name, hp, items in work]
+
+    one_pass()                                                  # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = one_pass()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    cells = {name: int(sum(r.n_cells for r in rs)) for name, rs in out}
+    h = hashlib.sha256()
+    for _, rs in out:
+        for r in rs:
+            h.update(r.label.numpy().tobytes()); h.update(r.confidence.numpy().tobytes())
+    total = sum(cells.values())
+    return {"what": f"{per_group * 4} synthetic {S}x{S} images in four batch CSVs of {per_group} (full-15 -> vit_l, structure-7, "
+                    "DAPI/CD45/GFAP -> nerve, structure + GFAP -> structure & nerve vote), image i of a CSV on rank i mod N, "
+                    "pinned host images in, every image's labels / confidences / counts on the host of every rank",
+            "n_gpus": world, "images": per_group * 4, "cells": total, "cells_per_group": cells, "ms": ms,
+            "value": total / (ms / 1000), "unit": "cells/s", "h2d_bytes_this_rank": int(h2d),
+            "labels_confidences_sha256": h.hexdigest()}
 
 
 if __name__ == "__main__":

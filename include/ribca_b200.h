@@ -52,9 +52,11 @@ enum ribca_precision {
   RIBCA_F16F8 = 3   /* fp16 main pass + one e4m3 pass over a doubled K axis that carries both first-order
                        correction terms (a_lo*w_hi + a_hi*w_lo): two passes' worth of tensor time, relative
                        error ~2^-15 per product (measured max |dprob| 1.3e-4): default                    */
+  , RIBCA_FP32 = 4  /* plain fp32 operands and fp32 FMA accumulation on the FP32 pipe (the reference's own arithmetic,
+                       cta/model.py:397-406): last level of the exact-label re-evaluation; weights = RIBCA_PLANES_F32 */
 };
-/* 16-bit operand plane formats (see csrc/common.cuh) */
-enum ribca_plane_format { RIBCA_PLANES_BF16 = 0, RIBCA_PLANES_F16F8 = 1 };
+/* operand formats of the packed GEMM weights: two 16-bit planes (see csrc/common.cuh) or plain fp32 matrices */
+enum ribca_plane_format { RIBCA_PLANES_BF16 = 0, RIBCA_PLANES_F16F8 = 1, RIBCA_PLANES_F32 = 2 };
 
 const char* ribca_last_error(void);
 int ribca_version(void);
@@ -72,7 +74,8 @@ long long ribca_launch_count(void);
 #define RIBCA_PROF_CELLSTATS 4   /* ribca_cell_stats;           work = H*W*4 bytes                    */
 #define RIBCA_PROF_LAYERNORM 5   /* work = M*D*8 bytes                                                */
 #define RIBCA_PROF_MERGE 6       /* work = n*(4*classes+5) bytes                                      */
-#define RIBCA_PROF_CLASSES 7
+#define RIBCA_PROF_GEMM_F32 7    /* sgemm_nt_kernel of the RIBCA_FP32 re-evaluation; work = 2*M*N*K FLOP */
+#define RIBCA_PROF_CLASSES 8
 int ribca_profile_begin(void);
 int ribca_profile_end(double* ms, long long* launches, double* work, int n_classes);
 
@@ -275,12 +278,16 @@ int ribca_mae_impute(const ribca_mae_desc* desc, const float* wf32, const void* 
  * (tie-break: first maximum in that order for two models; class-index order for one model).
  * h_type_thresh[18] = cell_type_confidence values; confidence = global threshold.
  * Outputs: label[n] (uint8 global type), conf[n] (float32, -1 when re-labelled "Others"),
- * counts[18] (int64, accumulated: caller zeroes).
+ * counts[18] (int64, accumulated: caller zeroes; may be null), margin[n] (float32, may be null): the decision
+ * margin of the cell = the smallest change of its probabilities that could change (label, re-labelled?) -
+ * min(|winner - its threshold|, gap to every candidate that would give another outcome).  Cells whose margin
+ * is below the error bound of a reduced-precision forward are re-evaluated at higher precision by the host
+ * (pipeline.refine_labels), which is what makes the labels of cta/model.py:481-636 exact by construction.
  */
 int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_class0,
                       const float* probs1, int classes1, const int* h_type_of_class1, int n_cells,
                       const int* h_vote_rank, const float* h_type_thresh, float confidence,
-                      uint8_t* label, float* conf, long long* counts, ribca_stream_t stream);
+                      uint8_t* label, float* conf, long long* counts, float* margin, ribca_stream_t stream);
 
 /* Per-pixel map from per-cell values (label / colour / confidence maps of Annotator.colorize,
  * cta/model.py:806-858): out[p*channels + c] = mask[p] > 0 ? cell_value[id_to_index[mask[p]]*channels + c] : 0. */

@@ -135,7 +135,7 @@ SIGNATURES = {
     "ribca_neighbor_stats": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_I), _I, _P, _P]),
     "ribca_paint_cells": (_I, [_P, _LL, _P, _I, _P, _I, _P, _P]),
     "ribca_merge_votes": (_I, [_P, _I, C.POINTER(_I), _P, _I, C.POINTER(_I), _I, C.POINTER(_I), C.POINTER(_F), _F,
-                               _P, _P, _P, _P]),
+                               _P, _P, _P, _P, _P]),
 }
 
 

@@ -38,13 +38,16 @@ class MarkerImputer():
         self.channel_number = spec.channels
         self.model = MaeEngine(spec, state, device=device)
 
-    def impute(self, data, batch_size=1):
+    def impute(self, data, batch_size=1, precision=None):
         """data: (N, C_panel, 40, 40) float32.  A CUDA tensor is imputed in place; a CPU tensor makes
         the round trip the reference makes (markerImputer.py:301,317).  `batch_size` is accepted for
-        signature compatibility; the engine picks its own chunking."""
+        signature compatibility; the engine picks its own chunking.  `precision` (not in the reference) selects a
+        higher-precision pass for the exact-label re-evaluation."""
+        if precision is not None and precision not in self.model.PRECISIONS:
+            precision = "bf16x3"
         if data.is_cuda:
-            return self.model.impute(data, self.channel_index)
+            return self.model.impute(data, self.channel_index, precision=precision)
         dev = data.to(self.device, torch.float32).contiguous()
-        self.model.impute(dev, self.channel_index)
+        self.model.impute(dev, self.channel_index, precision=precision)
         data.copy_(dev.cpu())
         return data

@@ -17,7 +17,7 @@ import os
 import numpy as np
 import torch
 
-from .. import ops
+from .. import exact, ops
 from ..engine import VitEngine
 from ..parallel import all_gather_rows, all_reduce_sum, world
 from ..weights import MODEL_DIR, VIT_SPECS, load_checkpoint
@@ -63,10 +63,10 @@ def merge_branch(panels):
     raise ValueError("No predictions to merge")
 
 
-def merge_on_device(probs: dict, confidence, cell_type_confidence=None):
+def merge_on_device(probs: dict, confidence, cell_type_confidence=None, want_margin: bool = False):
     """merge_by_voting for one image on the device: probs maps panel -> (n, classes) float32 CUDA
     tensor.  Returns (label uint8 index into ALL_TYPES, conf float32 with -1 for re-labelled cells,
-    counts int64[18])."""
+    counts int64[18]) and, with want_margin, every cell's decision margin (exact.refine_labels)."""
     used = merge_branch(probs.keys())
     ctc = cell_type_confidence or {}
     thresh = [float(ctc.get(t, -1)) for t in ALL_TYPES]
@@ -74,7 +74,7 @@ def merge_on_device(probs: dict, confidence, cell_type_confidence=None):
     p1 = probs[used[1]] if len(used) > 1 else None
     t1 = types[1] if len(used) > 1 else None
     return ops.merge_votes(probs[used[0]].contiguous(), types[0], None if p1 is None else p1.contiguous(), t1,
-                           _VOTE_RANK, thresh, confidence)
+                           _VOTE_RANK, thresh, confidence, want_margin=want_margin)
 
 
 class _AnnotationRows:
@@ -148,6 +148,8 @@ class Annotator(object):
         self.cell_type_confidence = ({t: -1 for t in ALL_TYPES} if cell_type_confidence is None else cell_type_confidence)
         self.models = {}
         self.precision = os.environ.get("RIBCA_PRECISION", ops.DEFAULT_PRECISION)
+        self.exact_labels = exact.LEVELS         # levels of margin-guarded re-evaluation (RIBCA_EXACT_LABELS, default 2)
+        self.refine_stats = []                   # per image: exact.RefineStats of this rank's cells
 
     # ---- stage 1-3 ---------------------------------------------------------------------------------
     def preprocess(self):
@@ -207,8 +209,15 @@ class Annotator(object):
                         parts[p].append(self.models[p].forward(batch[p]))
                 local = {p: torch.cat(v) if v else torch.empty((0, len(VIT_SPECS[p].classes)), device=pre.device)
                          for p, v in parts.items()}
-            # stage 5 on this rank's cells, then the single gather
-            label, conf, counts = merge_on_device(local, self.confidence_thresh, self.cell_type_confidence)
+            # stage 5 on this rank's cells (+ the margin-guarded re-evaluation that makes the labels independent of the
+            # fast path's rounding, exact.py), then the single gather
+            label, conf, counts, _, stats = exact.refine_labels(
+                local, lambda pr, want_margin=True: merge_on_device(pr, self.confidence_thresh, self.cell_type_confidence,
+                                                                    want_margin=want_margin),
+                lambda sel, prec, i=i: {p: self.models[p].forward(t, precision=prec)
+                                        for p, t in pre.patches_of_cells(i, sel, panels, prec).items()},
+                levels=self.exact_labels)
+            self.refine_stats.append(stats)
             label = all_gather_rows(label, n_total, lo, hi)
             conf = all_gather_rows(conf, n_total, lo, hi)
             counts = all_reduce_sum(counts)

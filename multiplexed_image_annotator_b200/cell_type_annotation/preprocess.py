@@ -191,6 +191,21 @@ class ImageProcessor(object):
                     imp.impute(batch[p], 64)
             yield a, b, batch, avg
 
+    def patches_of_cells(self, i, sel, panels, precision=None):
+        """Model inputs of the cells `sel` (int64 device tensor, indices into this rank's range of image i) for
+        `panels`, imputed at `precision`: what exact.refine_labels re-evaluates."""
+        lo, _ = self.cell_range[i]
+        sub = self.cells[i].subset(sel + lo)
+        idx = [self.parser.indices[p] for p in panels]
+        outs, _, _ = ops.build_patches(self.images_dev[i], self.masks_dev[i], self.min_val[i], sub, idx, 0, sub.n,
+                                       cell_size=self.cell_size)
+        batch = dict(zip(panels, outs))
+        for p in panels:
+            imp = self._imputer_for(p)
+            if imp is not None:
+                imp.impute(batch[p], 64, precision=precision)
+        return batch
+
     # ---- the reference's driver ----------------------------------------------------------------------
     def transform(self):
         rank, nranks = world()

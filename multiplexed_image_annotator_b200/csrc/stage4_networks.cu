@@ -18,6 +18,9 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
 int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads, int hd,
                         void* out_split, long long out_plane, int out_fmt, cudaStream_t st);
 
+int vit_forward_f32(const ribca_vit_desc* desc, const float* wf32, const float* wmat, const float* patches, int n_cells,
+                    float* probs, float* logits, float* x, float* a, float* qkv, float* h, cudaStream_t st);
+
 static inline int fmt_of(int precision) { return precision == RIBCA_F16F8 ? kFmtF16F8 : kFmtBf16; }
 
 typedef __nv_bfloat16 bf16;
@@ -320,6 +323,13 @@ head_softmax_kernel(const float* __restrict__ x, int n_cells, int tokens, int D,
   }
 }
 
+int head_softmax_launch(const float* x, int n_cells, int tokens, int D, const float* gamma, const float* beta, float eps,
+                        const float* head_w, const float* head_b, int classes, float* probs, float* logits, cudaStream_t st) {
+  head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x, n_cells, tokens, D, gamma, beta, eps, head_w, head_b, classes, probs, logits);
+  RIBCA_LAUNCH_CHECK("head_softmax_kernel");
+  return RIBCA_OK;
+}
+
 // ---- MAE glue ---------------------------------------------------------------------------------
 struct PresentList { int n; int idx[RIBCA_MAX_PANEL_CH]; int rank[RIBCA_MAX_PANEL_CH]; };
 
@@ -587,6 +597,12 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
   Carver cv{static_cast<char*>(workspace), 0};
   BlockBuffers b;
   block_buffers(cv, b, M, D, desc->heads);
+  if (precision == RIBCA_FP32) {          // the reference's own arithmetic on the FP32 pipe (stage4_fp32.cu)
+    RIBCA_REQUIRE(desc->plane_format == RIBCA_PLANES_F32, "ribca_vit_forward: RIBCA_FP32 needs fp32 weight matrices (plane format %d given)",
+                  desc->plane_format);
+    return vit_forward_f32(desc, wf32, static_cast<const float*>(wsplit_), patches, n_cells, probs, logits, b.x,
+                           reinterpret_cast<float*>(b.a), b.qkv, reinterpret_cast<float*>(b.h), st);
+  }
   // patch embedding: im2col into the (larger) MLP buffer, GEMM with the cls/pos/bias row table
   const int Kpe = 16 * C;
   const long long pe_plane = M * Kpe;

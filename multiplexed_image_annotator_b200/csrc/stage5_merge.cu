@@ -26,10 +26,24 @@ struct MergeParams {
   float confidence;
 };
 
+// Decision margin (the guard of the exact-label re-evaluation, pipeline.refine_labels): the smallest perturbation of
+// the probabilities that could change the OUTCOME of the cell = (label, "was re-labelled Others").  With the winner k
+// (value v_k, threshold thr_k) and every other candidate j that could win instead:
+//   m_thr  = |v_k - thr_k|                                   (the winner crossing its threshold; not for the class "Others")
+//   m_j    = v_k - v_j                    if candidate j would give another outcome at its current value,
+//            max(v_k - v_j, |v_j - thr_j|) otherwise           (j must both overtake k and cross its own threshold)
+//   margin = min(m_thr, min_j m_j)
+// A cell whose margin exceeds twice the error bound of the probabilities has the same outcome in exact arithmetic.
+__device__ __forceinline__ int outcome_of(int type, float v, float thr, bool single) {
+  // single model: "Others" is a class of its own and is never re-labelled; two models: every winner is thresholded
+  if (single) return (type != kOthers && v < thr) ? (kOthers | 32) : type;
+  return v < thr ? (kOthers | 32) : type;
+}
+
 __global__ void __launch_bounds__(256)
 merge_votes_kernel(const float* __restrict__ p0, const float* __restrict__ p1, int n,
                    const __grid_constant__ MergeParams prm, uint8_t* __restrict__ label,
-                   float* __restrict__ conf, long long* __restrict__ counts) {
+                   float* __restrict__ conf, long long* __restrict__ counts, float* __restrict__ margin) {
   __shared__ int hist[kTypes];
   if (threadIdx.x < kTypes) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -37,6 +51,7 @@ merge_votes_kernel(const float* __restrict__ p0, const float* __restrict__ p1, i
   if (i < n) {
     int best;
     float value;
+    float mg = INFINITY;
     if (p1 == nullptr) {
       const float* row = p0 + (long long)i * prm.classes[0];
       int k = 0;
@@ -49,6 +64,20 @@ merge_votes_kernel(const float* __restrict__ p0, const float* __restrict__ p1, i
       const float t = prm.type_thresh[best];
       const float thr = t > 0.0f ? t : prm.confidence;
       value = pk;
+      if (margin) {
+        const int out_k = outcome_of(best, pk, thr, true);
+        if (best != kOthers) mg = fabsf(pk - thr);
+        for (int c = 0; c < prm.classes[0]; ++c) {
+          if (c == k) continue;
+          const int tj = prm.type_of_class[0][c];
+          const float tt = prm.type_thresh[tj];
+          const float thr_j = tt > 0.0f ? tt : prm.confidence;
+          const float vj = row[c];
+          float mj = pk - vj;
+          if (outcome_of(tj, vj, thr_j, true) == out_k) mj = tj == kOthers ? INFINITY : fmaxf(mj, fabsf(vj - thr_j));
+          mg = fminf(mg, mj);
+        }
+      }
       if (best != kOthers && pk < thr) { best = kOthers; value = -1.0f; }
     } else {
       float vote[kTypes];
@@ -71,15 +100,30 @@ merge_votes_kernel(const float* __restrict__ p0, const float* __restrict__ p1, i
       }
       const float t = prm.type_thresh[best];
       // Python min(o1, o2, confidence): first minimal element, float32 comparisons
-      float thr = others[0];
-      if (others[1] < thr) thr = others[1];
-      if (prm.confidence < thr) thr = prm.confidence;
-      if (!(t < 0.0f)) thr = t;
+      float thr_min = others[0];
+      if (others[1] < thr_min) thr_min = others[1];
+      if (prm.confidence < thr_min) thr_min = prm.confidence;
+      const float thr = !(t < 0.0f) ? t : thr_min;
       value = bv;
+      if (margin) {
+        const int out_k = outcome_of(best, bv, thr, false);
+        mg = fabsf(bv - thr);
+        for (int q = 0; q < kTypes - 1; ++q) {
+          const int tj = prm.order[q];
+          if (tj == best) continue;
+          const float tt = prm.type_thresh[tj];
+          const float thr_j = !(tt < 0.0f) ? tt : thr_min;
+          const float vj = vote[tj];
+          float mj = bv - vj;
+          if (outcome_of(tj, vj, thr_j, false) == out_k) mj = fmaxf(mj, fabsf(vj - thr_j));
+          mg = fminf(mg, mj);
+        }
+      }
       if (bv < thr) { best = kOthers; value = -1.0f; }
     }
     label[i] = (uint8_t)best;
     conf[i] = value;
+    if (margin) margin[i] = mg;
     atomicAdd(&hist[best], 1);
   }
   __syncthreads();
@@ -118,7 +162,7 @@ extern "C" int ribca_paint_cells(const int32_t* mask, long long n_pixels, const 
 extern "C" int ribca_merge_votes(const float* probs0, int classes0, const int* h_type_of_class0,
                                  const float* probs1, int classes1, const int* h_type_of_class1, int n_cells,
                                  const int* h_vote_rank, const float* h_type_thresh, float confidence,
-                                 uint8_t* label, float* conf, long long* counts, ribca_stream_t stream) {
+                                 uint8_t* label, float* conf, long long* counts, float* margin, ribca_stream_t stream) {
   RIBCA_REQUIRE(probs0 && h_type_of_class0 && h_vote_rank && h_type_thresh && label && conf,
                 "ribca_merge_votes: null pointer");
   RIBCA_REQUIRE(classes0 > 0 && classes0 <= kMaxClasses, "ribca_merge_votes: classes0=%d", classes0);
@@ -146,7 +190,7 @@ extern "C" int ribca_merge_votes(const float* probs0, int classes0, const int* h
   prm.confidence = confidence;
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_MERGE, (double)n_cells * (4.0 * (prm.classes[0] + prm.classes[1]) + 5.0), as_stream(stream));
-  merge_votes_kernel<<<(n_cells + 255) / 256, 256, 0, as_stream(stream)>>>(probs0, probs1, n_cells, prm, label, conf, counts);
+  merge_votes_kernel<<<(n_cells + 255) / 256, 256, 0, as_stream(stream)>>>(probs0, probs1, n_cells, prm, label, conf, counts, margin);
   if (prof) prof_end_span(as_stream(stream));
   RIBCA_LAUNCH_CHECK("merge_votes_kernel");
   return RIBCA_OK;

@@ -41,14 +41,41 @@ class _Packer:
         self.mat_off += p.numel()
         return off
 
-    def finish(self, device, fmt: int = ops.FMT_BF16):
-        """-> (fp32 blob, (2, total) 16-bit weight planes, plane stride, w_log2_scale)."""
-        wf32 = torch.cat(self.f32).to(device)
-        mats = torch.cat(self.mat).to(device)
-        if fmt == ops.FMT_BF16:
-            return wf32, ops.split_bf16(mats), self.mat_off, 0
-        t = ops.weight_log2_scale(float(mats.abs().max().item()))
-        return wf32, ops.split_planes(mats, fmt, w_role=True, log2_scale=t), self.mat_off, t + 8
+    def finish(self, device):
+        """-> (fp32 parameter blob on the device, fp32 GEMM matrices on the HOST: packed per format on demand)."""
+        return torch.cat(self.f32).to(device), torch.cat(self.mat)
+
+
+def pack_matrices(mats_host: torch.Tensor, fmt: int, device):
+    """GEMM matrices -> (device operand blob, w_log2_scale) in `fmt`: two 16-bit planes (2, total) for the tensor-core
+    formats, the plain fp32 blob for RIBCA_PLANES_F32 (the FP32-pipe re-evaluation path)."""
+    mats = mats_host.to(device)
+    if fmt == ops.FMT_F32:
+        return mats, 0
+    if fmt == ops.FMT_BF16:
+        return ops.split_bf16(mats), 0
+    t = ops.weight_log2_scale(float(mats.abs().max().item()))
+    return ops.split_planes(mats, fmt, w_role=True, log2_scale=t), t + 8
+
+
+class _Packs:
+    """The packed weights of one network per operand format, built lazily: the default precision at construction, the
+    higher-precision formats the first time a re-evaluation asks for them (pipeline.refine_labels)."""
+
+    def __init__(self, desc, mats_host, plane_elems, device):
+        self._desc, self._mats, self._plane, self._device = desc, mats_host, plane_elems, device
+        self._by_fmt = {}
+
+    def get(self, precision: str):
+        """-> (descriptor for this format, operand blob)."""
+        fmt = ops.plane_format(precision)
+        if fmt not in self._by_fmt:
+            d = type(self._desc)()
+            C.memmove(C.byref(d), C.byref(self._desc), C.sizeof(d))
+            blob, d.w_log2_scale = pack_matrices(self._mats, fmt, self._device)
+            d.plane_format, d.split_plane = fmt, self._plane
+            self._by_fmt[fmt] = (d, blob)
+        return self._by_fmt[fmt]
 
 
 def _pad_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
@@ -117,9 +144,9 @@ class VitEngine:
         d.head_w = pk.add_f32(sd["head.weight"]); d.head_b = pk.add_f32(sd["head.bias"])
         for i in range(s.depth):
             _pack_block(pk, sd, f"blocks.{i}", d.blocks[i], s.heads)
-        d.plane_format = ops.plane_format(precision)
-        self.wf32, self.wsplit, d.split_plane, d.w_log2_scale = pk.finish(self.device, d.plane_format)
-        self.desc = d
+        self.wf32, mats = pk.finish(self.device)
+        self._packs = _Packs(d, mats, pk.mat_off, self.device)
+        self.desc, self.wsplit = self._packs.get(precision)
 
     def set_head(self, weight: torch.Tensor, bias: torch.Tensor):
         """Replace the classification head in place (used by the calibration recipe)."""
@@ -139,11 +166,12 @@ class VitEngine:
         probs = torch.empty((n, k), dtype=torch.float32, device=self.device)
         logits = torch.empty((n, k), dtype=torch.float32, device=self.device) if return_logits else None
         prec = ops.PRECISION[precision or self.precision]
+        desc, wsplit = self._packs.get(precision or self.precision)
         for i in range(0, n, self.max_cells):
             m = min(self.max_cells, n - i)
-            ws_bytes = L.ribca_vit_workspace_bytes(C.byref(self.desc), m)
+            ws_bytes = L.ribca_vit_workspace_bytes(C.byref(desc), m)
             ws = _WS.get(ws_bytes, self.device)
-            _lib.check(L.ribca_vit_forward(C.byref(self.desc), ops._ptr(self.wf32), ops._ptr(self.wsplit),
+            _lib.check(L.ribca_vit_forward(C.byref(desc), ops._ptr(self.wf32), ops._ptr(wsplit),
                                            ops._ptr(patches[i:i + m]), m, ops._ptr(probs[i:i + m]),
                                            ops._ptr(logits[i:i + m]) if logits is not None else 0,
                                            ops._ptr(ws), ws.numel(), prec, ops._stream()), "ribca_vit_forward")
@@ -152,6 +180,7 @@ class VitEngine:
 
 class MaeEngine:
     """One panel's MAE marker imputer (reference markerImputer.py:69-329) resident on a CUDA device."""
+    PRECISIONS = ("f16f8", "bf16x3", "bf16x1", "bf16", "simt")
 
     def __init__(self, spec: MaeSpec | str, state_dict: dict, device="cuda", precision: str = ops.DEFAULT_PRECISION,
                  max_cells_per_call: int = 8192):
@@ -180,9 +209,9 @@ class MaeEngine:
             _pack_block(pk, sd, f"blocks.{i}", d.enc_blocks[i], s.enc_heads)
         for i in range(s.dec_depth):
             _pack_block(pk, sd, f"decoder_blocks.{i}", d.dec_blocks[i], s.dec_heads)
-        d.plane_format = ops.plane_format(precision)
-        self.wf32, self.wsplit, d.split_plane, d.w_log2_scale = pk.finish(self.device, d.plane_format)
-        self.desc = d
+        self.wf32, mats = pk.finish(self.device)
+        self._packs = _Packs(d, mats, pk.mat_off, self.device)
+        self.desc, self.wsplit = self._packs.get(precision)
 
     @torch.no_grad()
     def impute(self, patches: torch.Tensor, present, precision: str | None = None) -> torch.Tensor:
@@ -196,11 +225,12 @@ class MaeEngine:
         L = _lib.lib()
         arr = (C.c_int * len(present))(*present)
         prec = ops.PRECISION[precision or self.precision]
+        desc, wsplit = self._packs.get(precision or self.precision)
         for i in range(0, n, self.max_cells):
             m = min(self.max_cells, n - i)
-            ws_bytes = L.ribca_mae_workspace_bytes(C.byref(self.desc), m)
+            ws_bytes = L.ribca_mae_workspace_bytes(C.byref(desc), m)
             ws = _WS.get(ws_bytes, self.device)
-            _lib.check(L.ribca_mae_impute(C.byref(self.desc), ops._ptr(self.wf32), ops._ptr(self.wsplit),
+            _lib.check(L.ribca_mae_impute(C.byref(desc), ops._ptr(self.wf32), ops._ptr(wsplit),
                                           ops._ptr(patches[i:i + m]), m, arr, len(present), ops._ptr(ws), ws.numel(),
                                           prec, ops._stream()), "ribca_mae_impute")
         return patches

@@ -17,13 +17,14 @@ from . import _lib
 PATCH = 40
 MAX_PANEL_CH = 16
 GAUSS_STRIDE = 16
-PRECISION = {"bf16x3": 0, "bf16": 1, "bf16x1": 1, "simt": 2, "fp32": 2, "f16f8": 3}
+PRECISION = {"bf16x3": 0, "bf16": 1, "bf16x1": 1, "simt": 2, "f16f8": 3, "fp32": 4}
 DEFAULT_PRECISION = "f16f8"
-FMT_BF16, FMT_F16F8 = 0, 1                      # ribca_plane_format
+FMT_BF16, FMT_F16F8, FMT_F32 = 0, 1, 2          # ribca_plane_format
 
 
 def plane_format(precision: str) -> int:
-    return FMT_F16F8 if PRECISION[precision] == 3 else FMT_BF16
+    code = PRECISION[precision]
+    return FMT_F16F8 if code == 3 else (FMT_F32 if code == 4 else FMT_BF16)
 
 
 def weight_log2_scale(max_abs: float) -> int:
@@ -208,6 +209,11 @@ class CellTable:
     def __init__(self, ids, bbox, sums, count, id_to_index, n, max_id):
         self.ids, self.bbox, self.sums, self.count = ids, bbox, sums, count
         self.id_to_index, self.n, self.max_id = id_to_index, n, max_id
+
+    def subset(self, idx: torch.Tensor) -> "CellTable":
+        """The table rows `idx` (int64 device tensor) as a table of their own - the cells of a re-evaluation batch."""
+        return CellTable(self.ids[idx].contiguous(), self.bbox[idx].contiguous(), self.sums[idx].contiguous(),
+                         self.count[idx].contiguous(), self.id_to_index, int(idx.numel()), self.max_id)
 
     def centroids(self) -> torch.Tensor:
         """np.mean of the pixel lists: exact integer sums, one float64 division (model.py:785-786)."""
@@ -426,24 +432,26 @@ def attention_tc(qkv_split: torch.Tensor, cells: int, tokens: int, heads: int, h
 # ------------------------------------------------------------------------------------------------
 # stage 5
 # ------------------------------------------------------------------------------------------------
-def merge_votes(probs0, types0, probs1, types1, vote_rank, type_thresh, confidence):
-    """Returns (label uint8 (n,), conf float32 (n,), counts int64 (18,))."""
+def merge_votes(probs0, types0, probs1, types1, vote_rank, type_thresh, confidence, want_margin: bool = False):
+    """Returns (label uint8 (n,), conf float32 (n,), counts int64 (18,)) and, with want_margin, the decision margin
+    float32 (n,) of every cell (include/ribca_b200.h: ribca_merge_votes)."""
     _need_cuda(probs0, probs1)
     n, k0 = probs0.shape
     dev = probs0.device
     label = torch.empty(n, dtype=torch.uint8, device=dev)
     conf = torch.empty(n, dtype=torch.float32, device=dev)
     counts = torch.zeros(18, dtype=torch.int64, device=dev)
+    margin = torch.empty(n, dtype=torch.float32, device=dev) if want_margin else None
     if n == 0:
-        return label, conf, counts
+        return (label, conf, counts, margin) if want_margin else (label, conf, counts)
     t0 = (C.c_int * len(types0))(*types0)
     k1 = 0 if probs1 is None else probs1.shape[1]
     t1 = (C.c_int * max(k1, 1))(*(types1 or [0]))
     vr = (C.c_int * 18)(*vote_rank)
     tt = (C.c_float * 18)(*type_thresh)
     _lib.check(_lib.lib().ribca_merge_votes(_ptr(probs0), k0, t0, _ptr(probs1), k1, t1, n, vr, tt, float(confidence),
-                                            _ptr(label), _ptr(conf), _ptr(counts), _stream()), "ribca_merge_votes")
-    return label, conf, counts
+                                            _ptr(label), _ptr(conf), _ptr(counts), _ptr(margin), _stream()), "ribca_merge_votes")
+    return (label, conf, counts, margin) if want_margin else (label, conf, counts)
 
 
 def paint_cells(mask: torch.Tensor, cells: CellTable, cell_value: torch.Tensor) -> torch.Tensor:

@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import ops
+from . import exact, ops
 from .cell_type_annotation.model import ALL_TYPES, merge_on_device
 from .engine import MaeEngine, VitEngine
 from .parallel import all_gather_rows, all_reduce_sum, image_owner, shard_range, share_image_results, world
@@ -24,12 +24,41 @@ class HotPathResult:
     counts: torch.Tensor           # int64 (18,)
     probs: dict = field(default_factory=dict)
     cells: object = None
+    margin: torch.Tensor = None    # float32 (n,) decision margins of this rank's cells (after re-evaluation)
+    refine: object = None          # exact.RefineStats of this rank's cells
+    phases: object = None          # _Phases (run(..., time_phases=True)): device time of every phase of the step
 
     def names(self):
         return [ALL_TYPES[k] for k in self.label.cpu().tolist()]
 
 
-def normalize_over_ranks(image, device, blur, amax, rank, nranks) -> torch.Tensor:
+class _Phases:
+    """CUDA-event marks at the phase boundaries of one HotPath.run (bench.py's per-phase times of the strong-scaling
+    record).  mark(name) closes the phase `name`; ms() synchronises and returns {name: milliseconds}."""
+
+    def __init__(self, enabled: bool):
+        self.ev = None
+        if enabled:
+            self.ev = []
+            self.mark("start")
+
+    def mark(self, name: str):
+        if self.ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.append((name, e))
+
+    def ms(self) -> dict:
+        if not self.ev:
+            return {}
+        self.ev[-1][1].synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.ev[:-1], self.ev[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def normalize_over_ranks(image, device, blur, amax, rank, nranks, phases: _Phases | None = None) -> torch.Tensor:
     """Stage 1 of ONE image shared by the ranks: its channels are independent (reference preprocess.py:218-238), so rank r
     uploads and normalises channels c = r (mod N) only and each finished float32 plane is broadcast over NVLink from its
     owner - instead of every rank uploading and normalising the whole stack.  Same kernel on the same data: bit-identical."""
@@ -42,8 +71,12 @@ def normalize_over_ranks(image, device, blur, amax, rank, nranks) -> torch.Tenso
         plane = image[k:k + 1]
         plane = plane.to(device, non_blocking=True) if not plane.is_cuda else plane.contiguous()
         ops.normalize(plane, blur, amax, out=out[k:k + 1])
+    if phases is not None:
+        phases.mark("1_upload_normalize_own_channels")
     for k in range(c):
         dist.broadcast(out[k], src=k % nranks)
+    if phases is not None:
+        phases.mark("1b_plane_broadcasts")
     return out
 
 
@@ -54,7 +87,7 @@ class HotPath:
 
     def __init__(self, panels: dict, models: dict, imputers: dict | None = None, *, normalization=True, blur=0.3,
                  amax=99.8, confidence=0.3, cell_type_confidence=None, chunk_cells=4096, device="cuda",
-                 shard_cells=True, cell_size=30, shard_stage1=True):
+                 shard_cells=True, cell_size=30, shard_stage1=True, exact_labels: int | None = None):
         self.panels, self.models, self.imputers = dict(panels), models, imputers or {}
         self.normalization, self.blur, self.amax = normalization, blur, amax
         self.confidence, self.ctc = confidence, cell_type_confidence
@@ -63,12 +96,13 @@ class HotPath:
         self.shard_cells = shard_cells
         self.shard_stage1 = shard_stage1          # with shard_cells and > 1 rank: channels of stage 1 split over the ranks
         self.cell_size = cell_size
+        self.exact_labels = exact.LEVELS if exact_labels is None else exact_labels     # levels of margin-guarded re-evaluation
         for p in self.panels:
             if not isinstance(models.get(p), VitEngine):
                 raise ValueError(f"no classifier engine for panel {p}")
 
-    def _normalize_sharded(self, image, rank, nranks):
-        return normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks)
+    def _normalize_sharded(self, image, rank, nranks, phases=None):
+        return normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks, phases)
 
     def _to_device(self, a):
         if isinstance(a, np.ndarray):
@@ -76,14 +110,15 @@ class HotPath:
         return a if a.is_cuda else a.to(self.device, non_blocking=True)
 
     @torch.no_grad()
-    def run(self, image, mask, to_host: bool = True, keep_probs: bool = False) -> HotPathResult:
+    def run(self, image, mask, to_host: bool = True, keep_probs: bool = False, time_phases: bool = False) -> HotPathResult:
+        ph = _Phases(time_phases)
         msk = self._to_device(mask)
         if msk.dtype != torch.int32:
             msk = msk.to(torch.int32)
         host_img = torch.from_numpy(image) if isinstance(image, np.ndarray) else image
         rank, nranks = world() if self.shard_cells else (0, 1)
         if self.normalization and nranks > 1 and self.shard_stage1:
-            img = self._normalize_sharded(host_img, rank, nranks)
+            img = self._normalize_sharded(host_img, rank, nranks, ph)
         elif self.normalization and not host_img.is_cuda:
             img = ops.normalize_from_host(host_img, self.device, self.blur, self.amax)     # upload hidden behind stage 1
         else:
@@ -92,8 +127,10 @@ class HotPath:
                 img = ops.normalize(img, self.blur, self.amax)
             elif img.dtype != torch.float32:
                 img = img.to(torch.float32)
+        ph.mark("1_upload_normalize")
         cells = ops.cell_stats(msk)
         mn = ops.channel_min(img)
+        ph.mark("2_cell_stats")
         lo, hi = shard_range(cells.n, rank, nranks)
         names = list(self.panels)
         idx = [self.panels[p] for p in names]
@@ -108,24 +145,44 @@ class HotPath:
                 parts[p].append(self.models[p].forward(t))
         probs = {p: (torch.cat(v) if v else torch.empty((0, len(self.models[p].spec.classes)), device=self.device))
                  for p, v in parts.items()}
-        label, conf, counts = merge_on_device(probs, self.confidence, self.ctc)
+        ph.mark("3_4_patches_networks")
+
+        def forward_cells(sel, precision):
+            # model inputs of the selected cells of this rank's range, rebuilt (stage 3 is cheap) and run at `precision`
+            sub = cells.subset(sel + lo)
+            outs, _, _ = ops.build_patches(img, msk, mn, sub, idx, 0, sub.n, cell_size=self.cell_size)
+            res = {}
+            for p, t in zip(names, outs):
+                if p in self.imputers:
+                    eng, present = self.imputers[p]
+                    eng.impute(t, present, precision=precision if precision in eng.PRECISIONS else "bf16x3")
+                res[p] = self.models[p].forward(t, precision=precision)
+            return res
+
+        label, conf, counts, margin, stats = exact.refine_labels(
+            probs, lambda pr, want_margin=True: merge_on_device(pr, self.confidence, self.ctc, want_margin=want_margin),
+            forward_cells, levels=self.exact_labels)
+        ph.mark("5_merge_reevaluate")
         if nranks > 1:
             label = all_gather_rows(label, cells.n, lo, hi)
             conf = all_gather_rows(conf, cells.n, lo, hi)
             counts = all_reduce_sum(counts)
+            ph.mark("6_gather")
         if to_host:
             label, conf, counts = label.cpu(), conf.cpu(), counts.cpu()     # D2H ends the step (synchronises)
-        return HotPathResult(cells.n, label, conf, counts, probs if keep_probs else {}, cells)
+            ph.mark("7_results_to_host")
+        return HotPathResult(cells.n, label, conf, counts, probs if keep_probs else {}, cells, margin, stats, ph)
 
     @torch.no_grad()
     def run_batch(self, items, to_host: bool = True) -> list:
         """A batch of (image, mask) pairs (the batch-processing CSV): image i is annotated whole by rank i % world - no
         collective on the data path - and its owner broadcasts labels / confidences / counts at the end, so every rank
-        returns every image's HotPathResult (cells / probs only on the owner)."""
+        returns every image's HotPathResult (cells / probs only on the owner).  A rank may pass None for the images it
+        does not own (it never touches them)."""
         rank, nranks = world()
         shard_cells, self.shard_cells = self.shard_cells, False
         try:
-            own = [self.run(img, msk, to_host=False) if image_owner(i, nranks) == rank else None for i, (img, msk) in enumerate(items)]
+            own = [self.run(*item, to_host=False) if image_owner(i, nranks) == rank else None for i, item in enumerate(items)]
         finally:
             self.shard_cells = shard_cells
         shared = share_image_results([None if r is None else (r.label, r.confidence, r.counts) for r in own], self.device)

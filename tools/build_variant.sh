@@ -1,5 +1,5 @@
 #!/bin/bash
-# build an A/B variant of libribca_b200.so with extra nvcc flags.  usage: tools_build_variant.sh <name> <flags...>
+# build an A/B variant of libribca_b200.so with extra nvcc flags.  usage: tools/build_variant.sh <name> <flags...>
 # -> multiplexed_image_annotator_b200/build/libribca_<name>.so (load with RIBCA_LIB=...)
 set -e
 name=$1; shift

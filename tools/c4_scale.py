@@ -3,8 +3,8 @@
 whole hot path device-resident.  One GPU, or - under torchrun - the same image sharded by cell range over the ranks
 (every rank holds the image and runs stages 1-2, stages 3-5 on its range, one all-gather of labels / confidences at the end:
 STRONG scaling).  Prints cells/s (device time, max over ranks) and checks size-independent invariants.
-    python tools_c4_scale.py [S]
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29536 tools_c4_scale.py [S]"""
+    python tools/c4_scale.py [S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29536 tools/c4_scale.py [S]"""
 import hashlib, json, os, sys, time
 import torch
 import torch.distributed as dist

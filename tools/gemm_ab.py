@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B timing of libribca build variants on the block GEMM shapes: the variants are loaded side by side in one process
 and timed in interleaved rounds (the GPU is power-capped, so back-to-back runs of different processes are not comparable).
-usage: tools_gemm_ab.py <cells> <lib.so> [<lib.so> ...]"""
+usage: tools/gemm_ab.py <cells> <lib.so> [<lib.so> ...]"""
 import ctypes as C, statistics, sys, torch
 sys.path.insert(0, ".")
 from multiplexed_image_annotator_b200 import _lib, ops

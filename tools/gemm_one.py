@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One launch of each block GEMM shape per precision (for ncu captures).  usage: [PRECS=f16f8,bf16x3] tools_gemm_one.py <cells> [shape ...]"""
+"""One launch of each block GEMM shape per precision (for ncu captures).  usage: [PRECS=f16f8,bf16x3] tools/gemm_one.py <cells> [shape ...]"""
 import os, sys, torch
 sys.path.insert(0, ".")
 from multiplexed_image_annotator_b200 import ops

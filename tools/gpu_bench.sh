@@ -1,5 +1,5 @@
 #!/bin/bash
-# Bench + profiles on the GPU box.  usage: tools_gpu_bench.sh [tag]
+# Bench + profiles on the GPU box.  usage: tools/gpu_bench.sh [tag]
 # (the launch list uses the 1024^2 configuration: a full-size list costs ~19 GPU-minutes; the --set full captures use
 #  one launch of each block GEMM at the bench's chunk size (4096 cells, M = 413696) and one attention launch)
 tag=${1:-r01}
@@ -11,8 +11,8 @@ $SMALL > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$tag.csv $SMALL > gpurun_out/ncu_list_$tag.log 2>&1
 echo "ncu list exit $?"
 export PRECS=f16f8
-python tools_gemm_one.py 4096 qkv proj fc1 fc2 > gpurun_out/plain2_$tag.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -o gpurun_out/prof_gemm_$tag -f python tools_gemm_one.py 4096 qkv proj fc1 fc2 > gpurun_out/ncu_full_$tag.log 2>&1
+python tools/gemm_one.py 4096 qkv proj fc1 fc2 > gpurun_out/plain2_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -o gpurun_out/prof_gemm_$tag -f python tools/gemm_one.py 4096 qkv proj fc1 fc2 > gpurun_out/ncu_full_$tag.log 2>&1
 echo "ncu gemm exit $?"
 MID="python bench.py --size 2048 --steps 1 --warmup 1 --no-cpu-baseline"
 $MID > gpurun_out/plain3_$tag.log 2>&1 &&

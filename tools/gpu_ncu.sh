@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full capture of one kernel family.  usage: tools_gpu_ncu.sh <kernel-regex> <tag> [skip] [count]
+# ncu --set full capture of one kernel family.  usage: tools/gpu_ncu.sh <kernel-regex> <tag> [skip] [count]
 mkdir -p gpurun_out
 SMALL="python bench.py --size 1024 --steps 1 --warmup 1 --no-cpu-baseline"
 $SMALL > gpurun_out/plain_$2.log 2>&1 &&

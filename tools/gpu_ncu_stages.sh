@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full of one launch of each stage 1-3 / 5 / LayerNorm kernel (HBM-side evidence).  usage: tools_gpu_ncu_stages.sh <tag>
+# ncu --set full of one launch of each stage 1-3 / 5 / LayerNorm kernel (HBM-side evidence).  usage: tools/gpu_ncu_stages.sh <tag>
 tag=$1
 mkdir -p gpurun_out
 MID="python bench.py --size 2048 --steps 1 --warmup 1 --no-cpu-baseline"

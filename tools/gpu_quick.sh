@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick iteration: selected tests + short bench without the CPU baseline.  usage: tools_gpu_quick.sh "<pytest -k expr>" [bench args]
+# quick iteration: selected tests + short bench without the CPU baseline.  usage: tools/gpu_quick.sh "<pytest -k expr>" [bench args]
 mkdir -p gpurun_out
 k=$1; shift
 timeout 400 python -m pytest tests/test_gpu_networks.py -q -m gpu -k "$k" -p no:cacheprovider -x 2>&1 | tail -4

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise gpurun_out/ ncu artefacts into profiles/ (tracked).  usage: tools_profile_summary.py TAG"""
+"""Summarise gpurun_out/ ncu artefacts into profiles/ (tracked).  usage: tools/profile_summary.py TAG"""
 import collections, csv, re, subprocess, sys
 
 tag = sys.argv[1]
@@ -69,7 +69,7 @@ if gemm_rows:
     # one launch each of the qkv / proj / fc1 / fc2 GEMMs of a vit_l block at the bench's chunk size: their mean is the
     # per-launch DRAM traffic of the step's launch mix (each occurs once per block and chunk)
     n = len(gemm_rows)
-    traffic = {"source": f"ncu --set full, gpurun_out/prof_gemm_{tag}.ncu-rep (tools_gemm_one.py 4096 qkv proj fc1 fc2, f16f8)",
+    traffic = {"source": f"ncu --set full, gpurun_out/prof_gemm_{tag}.ncu-rep (tools/gemm_one.py 4096 qkv proj fc1 fc2, f16f8)",
                "launches": gemm_rows,
                "mean_dram_bytes_per_launch": sum(g["dram_read_bytes"] + g["dram_write_bytes"] for g in gemm_rows) / n,
                "mean_l2_to_sm_bytes_per_launch": sum(g["l2_to_sm_bytes"] for g in gemm_rows) / n}
