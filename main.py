@@ -13,12 +13,15 @@ import pandas as pd
 
 from multiplexed_image_annotator_b200.cell_type_annotation.gui_api import _intensity_dict, _pipeline
 from multiplexed_image_annotator_b200.cell_type_annotation.model import Annotator
+from multiplexed_image_annotator_b200.parallel import barrier, is_writer
 
 
 def run(marker_list_path, image_path, mask_path, device, main_dir, batch_id, bs, strict, infer, min_cells, n_regions,
         normalize, blur, amax, confidence, cell_size, cell_type_confidence, n_jobs):
     path_ = os.path.join(main_dir, "images.csv")
-    pd.DataFrame([[image_path, mask_path]]).to_csv(path_, index=False, header=["image_path", "mask_path"])
+    if is_writer():                               # ranks sharing main_dir (torchrun): rank 0 owns the file
+        pd.DataFrame([[image_path, mask_path]]).to_csv(path_, index=False, header=["image_path", "mask_path"])
+    barrier()
     annotator = Annotator(marker_list_path, path_, device, main_dir, batch_id, strict, infer, min_cells, normalize, blur,
                           amax, confidence, cell_size, cell_type_confidence, n_jobs=n_jobs)
     _pipeline(annotator, bs, n_regions, export_before_regions=True, from_script=True)

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pandas as pd
 
+from ..parallel import barrier, is_writer
 from .model import Annotator
 
 
@@ -42,11 +43,15 @@ def _intensity_dict(annotator):
 def gui_run(marker_list_path, image_path, mask_path, device, main_dir, batch_id, bs, strict, infer, min_cells, n_regions,
             normalize, blur, amax, confidence, cell_size, cell_type_confidence, n_jobs=0):
     path_ = os.path.join(main_dir, "images.csv")
-    pd.DataFrame([[image_path, mask_path]]).to_csv(path_, index=False, header=["image_path", "mask_path"])
+    if is_writer():                               # ranks sharing main_dir (torchrun): rank 0 owns the file
+        pd.DataFrame([[image_path, mask_path]]).to_csv(path_, index=False, header=["image_path", "mask_path"])
+    barrier()
     annotator = Annotator(marker_list_path, path_, device, main_dir, batch_id, strict, infer, min_cells, normalize, blur,
                           amax, confidence, cell_size, cell_type_confidence, n_jobs=n_jobs)
     _pipeline(annotator, bs, n_regions, export_before_regions=False, from_script=False)
-    os.remove(path_)
+    barrier()
+    if is_writer():
+        os.remove(path_)
     return _intensity_dict(annotator)
 
 

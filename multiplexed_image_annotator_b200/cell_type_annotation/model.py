@@ -19,7 +19,7 @@ import torch
 
 from .. import exact, ops
 from ..engine import VitEngine
-from ..parallel import all_gather_rows, all_reduce_sum, world
+from ..parallel import all_gather_rows, all_reduce_sum, barrier, broadcast_object, is_writer, world
 from ..weights import MODEL_DIR, VIT_SPECS, load_checkpoint
 from .logger import Logger
 from .markerParse import MarkerParser
@@ -218,6 +218,7 @@ class Annotator(object):
                                         for p, t in pre.patches_of_cells(i, sel, panels, prec).items()},
                 levels=self.exact_labels)
             self.refine_stats.append(stats)
+            pre.release(i)          # a stack that was re-read because it is outside the residency budget goes again
             label = all_gather_rows(label, n_total, lo, hi)
             conf = all_gather_rows(conf, n_total, lo, hi)
             counts = all_reduce_sum(counts)
@@ -264,7 +265,7 @@ class Annotator(object):
         """reference model.py:768-795, same file name, header, rounding and formatting."""
         if len(self.annotations) == 0:
             raise ValueError("No annotations to export")
-        for i in range(len(self.annotations)):
+        for i in range(len(self.annotations) if is_writer() else 0):      # every rank holds the same results: rank 0 writes
             f = os.path.join(self.result_dir, f"{self.batch_id}_annotation_{i}.csv")
             pos = self.preprocessor.cell_pos_dict[i]
             cent = pos.sums.astype(np.float64) / pos.count.astype(np.float64)[:, None]     # = np.mean of the lists
@@ -277,6 +278,7 @@ class Annotator(object):
                     region = "Region " + str(self.tissue_regions[i][key]) if hasattr(self, 'tissue_regions') else None
                     file.write(f"{key},{self.annotations[i][j]},{conf},{row},{col},{region}\n")
             self.logger.log(f"Exported annotations for image {i} to {f}")
+        barrier()
 
     def cell_type_composition(self, reduction=True, integrate=False):
         """reference model.py:861-912: the per-type counts / fractions (the pie chart itself is
@@ -316,6 +318,8 @@ class Annotator(object):
             self.heatmaps.append((celltypes, colormap))
             f = os.path.join(self.result_dir, f"{self.batch_id}_Integrated_heatmap.png" if integrate else f"{self.batch_id}_heatmap_{g}.png")
             try:
+                if not is_writer():
+                    continue
                 import matplotlib.pyplot as plt
                 import seaborn as sns
             except ImportError:
@@ -330,16 +334,20 @@ class Annotator(object):
     def neighborhood_analysis(self, n_neighbors=25, integrate=True, normalize=True):
         """reference model.py:798-800: the neighbourhood matrix CSV(s), from the GPU k-NN (the heat-map PNG is not drawn)."""
         from .spatial_methods import neighborhood_analysis
-        return neighborhood_analysis(self.annotations_all, n_neighbors=n_neighbors, cell_types=self.cell_types, integrate=integrate,
-                                     normalize=normalize, result_dir=self.result_dir, batch_id=self.batch_id,
-                                     device=self.preprocessor.device)
+        out = neighborhood_analysis(self.annotations_all, n_neighbors=n_neighbors, cell_types=self.cell_types, integrate=integrate,
+                                    normalize=normalize, result_dir=self.result_dir if is_writer() else None, batch_id=self.batch_id,
+                                    device=self.preprocessor.device)
+        barrier()
+        return out
 
     def tissue_region_analysis(self, n, method="kmeans"):
         """reference model.py:802-804."""
         from .spatial_methods import tissue_region_partition
         self.n_regions = n
-        self.tissue_regions = tissue_region_partition(self.annotations_all, n, self.n_jobs, method=method,
-                                                      device=self.preprocessor.device)
+        # the reference's KMeans is unseeded: rank 0 clusters, every rank gets ITS labels
+        regions = tissue_region_partition(self.annotations_all, n, self.n_jobs, method=method,
+                                          device=self.preprocessor.device) if is_writer() else None
+        self.tissue_regions = broadcast_object(regions)
 
     def colorize(self, from_script=False):
         """reference model.py:806-858: colourised label map, confidence map and (GUI runs) the uint8 label
@@ -353,13 +361,13 @@ class Annotator(object):
         if len(self.annotations) == 0:
             raise ValueError("No annotations to colorize")
         dev = pre.device
-        for i in range(len(pre.masks)):
+        for i in range(len(pre.masks) if is_writer() else 0):
             type_of_all = np.array([int(np.where(self.cell_types == t)[0][0]) if t in self.cell_types else 0 for t in ALL_TYPES])
             idx = torch.from_numpy(type_of_all[self.labels_index[i]].astype(np.uint8)).to(dev)           # index into cell_types
             rgb = torch.tensor(self.colors, dtype=torch.uint8, device=dev)[idx.long()]
             conf = [number_to_rgb(c) if c > 0 else [192, 192, 192] for c in self.confidence[i]]
             conf = torch.tensor(conf, dtype=torch.uint8, device=dev).reshape(-1, 3)
-            m, cells = pre.masks_dev[i], pre.cells[i]
+            m, cells = pre.mask_dev(i), pre.cells[i]
             Image.fromarray(ops.paint_cells(m, cells, rgb.contiguous()).cpu().numpy()).save(
                 os.path.join(self.result_dir, f"{self.batch_id}_colorized_annotation_{i}.png"))
             Image.fromarray(ops.paint_cells(m, cells, conf.contiguous()).cpu().numpy()).save(
@@ -377,13 +385,23 @@ class Annotator(object):
                 if not from_script and os.path.isdir("./src/multiplexed_image_annotator/cell_type_annotation/_working_dir_temp"):
                     Image.fromarray(ops.paint_cells(m, cells, (reg_d + 1).contiguous()).cpu().numpy()).save(
                         "./src/multiplexed_image_annotator/cell_type_annotation/_working_dir_temp/output_img_2.png")
+            pre.release(i)
+        barrier()
 
     def umap_visualization(self):
         self._skipped("umap_visualization")
 
     def clear_tmp(self):
-        if os.path.isdir(self.temp_dir):
+        barrier()                                   # no rank is still working in main_dir
+        if is_writer() and os.path.isdir(self.temp_dir):
             for f in os.listdir(self.temp_dir):
-                os.remove(os.path.join(self.temp_dir, f))
-            os.rmdir(self.temp_dir)
+                try:
+                    os.remove(os.path.join(self.temp_dir, f))
+                except FileNotFoundError:
+                    pass
+            try:
+                os.rmdir(self.temp_dir)
+            except (FileNotFoundError, OSError):
+                pass
         self.logger.log("Temporary files cleared")
+        barrier()

@@ -23,7 +23,8 @@ from ..io import is_tiff, iter_tiff_planes, read_image, read_mask
 from ..parallel import shard_range, world
 from .markerImputer import MarkerImputer
 
-PATCH_CACHE_BYTES = int(os.environ.get("RIBCA_PATCH_CACHE_BYTES", 48 << 30))
+PATCH_CACHE_BYTES = int(os.environ.get("RIBCA_PATCH_CACHE_BYTES", 48 << 30))      # all images of a batch together
+IMAGE_CACHE_BYTES = int(os.environ.get("RIBCA_IMAGE_CACHE_BYTES", 64 << 30))      # resident normalised stacks + masks
 CHUNK_CELLS = int(os.environ.get("RIBCA_CHUNK_CELLS", 8192))
 
 
@@ -102,10 +103,14 @@ class ImageProcessor(object):
         self.cell_pos_dict = []
         self.intensity_full = []
         os.makedirs(self.save_path, exist_ok=True)
-        for f in os.listdir(self.save_path):
-            fp = os.path.join(self.save_path, f)
-            if os.path.isfile(fp):
-                os.remove(fp)
+        if world()[0] == 0:                      # ranks sharing one main_dir: rank 0 owns the filesystem side effects
+            for f in os.listdir(self.save_path):
+                fp = os.path.join(self.save_path, f)
+                try:
+                    if os.path.isfile(fp):
+                        os.remove(fp)
+                except FileNotFoundError:
+                    pass
         self.infer = infer
         self.masks = []
         if str(device).startswith("cpu"):
@@ -120,6 +125,9 @@ class ImageProcessor(object):
         self.images_dev, self.masks_dev, self.cells, self.min_val = [], [], [], []
         self.patches = []          # per image: {panel: tensor} for this rank's cell range, or None (streamed)
         self.cell_range = []       # per image: (lo, hi) cells owned by this rank
+        self._resident = []        # per image: stack + mask stay on the device (inside IMAGE_CACHE_BYTES)
+        self._patch_bytes = 0      # bytes of cached patches over all images
+        self._image_bytes = 0      # bytes of resident stacks + masks over all images
         self._imputers = {}
         self.logger.log("\n")
         self.logger.log("Starting image processing...")
@@ -164,7 +172,9 @@ class ImageProcessor(object):
 
     @staticmethod
     def _positions(mask_host, tab, mask_dev=None):
-        src = (lambda: ops.cell_pixels(mask_dev, tab)) if mask_dev is not None else None
+        """mask_dev: the device mask, or a callable returning it (so that a released mask is uploaded again on demand)."""
+        get = mask_dev if callable(mask_dev) else (lambda: mask_dev)
+        src = (lambda: ops.cell_pixels(get(), tab)) if mask_dev is not None else None
         return CellPositions(mask_host, tab.ids.cpu().numpy(), tab.bbox.cpu().numpy(), tab.sums.cpu().numpy(),
                              tab.count.cpu().numpy(), src)
 
@@ -182,7 +192,7 @@ class ImageProcessor(object):
         idx = [self.parser.indices[p] for p in panels]
         for a in range(lo, hi, chunk):
             b = min(a + chunk, hi)
-            outs, avg, _ = ops.build_patches(self.images_dev[i], self.masks_dev[i], self.min_val[i], self.cells[i], idx,
+            outs, avg, _ = ops.build_patches(self.image_dev(i), self.mask_dev(i), self.min_val[i], self.cells[i], idx,
                                              a, b - a, want_intensity=want_intensity, cell_size=self.cell_size)
             batch = dict(zip(panels, outs))
             for p in panels:
@@ -196,52 +206,85 @@ class ImageProcessor(object):
         `panels`, imputed at `precision`: what exact.refine_labels re-evaluates."""
         lo, _ = self.cell_range[i]
         sub = self.cells[i].subset(sel + lo)
-        idx = [self.parser.indices[p] for p in panels]
-        outs, _, _ = ops.build_patches(self.images_dev[i], self.masks_dev[i], self.min_val[i], sub, idx, 0, sub.n,
-                                       cell_size=self.cell_size)
-        batch = dict(zip(panels, outs))
-        for p in panels:
+        cached = self.patches[i]
+        rebuilt = [p for p in panels if cached is None or self._imputer_for(p) is not None]     # imputed inputs start from the raw crop
+        batch = {p: cached[p][sel] for p in panels if p not in rebuilt}
+        if rebuilt:
+            idx = [self.parser.indices[p] for p in rebuilt]
+            outs, _, _ = ops.build_patches(self.image_dev(i), self.mask_dev(i), self.min_val[i], sub, idx, 0, sub.n,
+                                           cell_size=self.cell_size)
+            batch.update(zip(rebuilt, outs))
+        for p in rebuilt:
             imp = self._imputer_for(p)
             if imp is not None:
                 imp.impute(batch[p], 64, precision=precision)
         return batch
 
+    # ---- device residency of a batch (the reference bounds memory by spilling to tmp/*.pt, preprocess.py:132-135) -------
+    def _load_image(self, i):
+        """Decode image i and run stage 1: the normalised float32 stack on the device."""
+        import struct
+        rank, nranks = world()
+        image_path = self.image_paths[i]
+        img_dev = None
+        if self.normalization and nranks == 1 and is_tiff(image_path):
+            try:                                          # decode, upload and stage 1 overlapped plane by plane
+                img_dev = ops.normalize_from_planes(iter_tiff_planes(image_path), self.device, self.blur, self.amax)
+            except (ValueError, KeyError, struct.error, OSError):
+                img_dev = None                            # a TIFF flavour the reader does not take: whole-file decode below
+        if img_dev is not None:
+            return img_dev
+        image = read_image(image_path)
+        if self.normalization and nranks > 1:
+            from ..pipeline import normalize_over_ranks          # channels split over the ranks, planes broadcast
+            return normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks)
+        if self.normalization:
+            return ops.normalize_from_host(torch.from_numpy(image), self.device, self.blur, self.amax)
+        img_dev = torch.from_numpy(image).to(self.device, non_blocking=True)
+        return img_dev if img_dev.dtype == torch.float32 else img_dev.to(torch.float32)
+
+    def image_dev(self, i):
+        """Normalised stack of image i on the device; an image that was released to stay inside RIBCA_IMAGE_CACHE_BYTES is
+        decoded and normalised again (same kernels, same bits) and stays until `release(i)`."""
+        if self.images_dev[i] is None:
+            self.images_dev[i] = self._load_image(i)
+        return self.images_dev[i]
+
+    def mask_dev(self, i):
+        if self.masks_dev[i] is None:
+            self.masks_dev[i] = torch.from_numpy(self.masks[i]).to(self.device, non_blocking=True)
+        return self.masks_dev[i]
+
+    def release(self, i):
+        """Drop image i's device stack and mask if it is not one of the images the cache budget keeps resident."""
+        if not self._resident[i]:
+            self.images_dev[i] = None
+            self.masks_dev[i] = None
+
     # ---- the reference's driver ----------------------------------------------------------------------
     def transform(self):
+        """cta/preprocess.py:241-290.  Device memory of a batch is bounded: the patch cache is ONE budget over all images
+        (RIBCA_PATCH_CACHE_BYTES, default 48 GiB; images that do not fit are cropped again chunk by chunk in predict) and so
+        are the resident normalised stacks + masks (RIBCA_IMAGE_CACHE_BYTES, default 64 GiB; an image beyond it is released
+        after its statistics are taken and re-read from its file when predict needs it) - peak memory is one image plus
+        the two budgets, however long the CSV is."""
         rank, nranks = world()
         for i, (image_path, mask_path) in enumerate(zip(self.image_paths, self.mask_paths)):
             mask = read_mask(mask_path)                       # 2-D, int32 (preprocess.py:246-250)
             mask_dev = torch.from_numpy(mask).to(self.device, non_blocking=True)
-            img_dev = None
-            if self.normalization and nranks == 1 and is_tiff(image_path):
-                try:                                          # decode, upload and stage 1 overlapped plane by plane
-                    img_dev = ops.normalize_from_planes(iter_tiff_planes(image_path), self.device, self.blur, self.amax)
-                except (ValueError, KeyError):
-                    img_dev = None                            # a TIFF flavour the reader does not take: whole-file decode below
-            image = read_image(image_path) if img_dev is None else None
-            if img_dev is not None:
-                pass
-            elif self.normalization and nranks > 1:
-                from ..pipeline import normalize_over_ranks          # channels split over the ranks, planes broadcast
-                img_dev = normalize_over_ranks(image, self.device, self.blur, self.amax, rank, nranks)
-            elif self.normalization:
-                img_dev = ops.normalize_from_host(torch.from_numpy(image), self.device, self.blur, self.amax)
-            else:
-                img_dev = torch.from_numpy(image).to(self.device, non_blocking=True)
-                if img_dev.dtype != torch.float32:
-                    img_dev = img_dev.to(torch.float32)
+            img_dev = self._load_image(i)
             self.masks.append(mask)
             tab = ops.cell_stats(mask_dev)
             self.images_dev.append(img_dev)
             self.masks_dev.append(mask_dev)
             self.cells.append(tab)
             self.min_val.append(ops.channel_min(img_dev))
-            self.cell_pos_dict.append(self._positions(mask, tab, mask_dev))
+            self.cell_pos_dict.append(self._positions(mask, tab, lambda i=i: self.mask_dev(i)))
             self.cell_range.append(shard_range(tab.n, rank, nranks))
             panels = self.predicted_panels()
             lo, hi = self.cell_range[i]
             per_cell = sum(len(self.parser.indices[p]) for p in panels) * 40 * 40 * 4
-            keep = (hi - lo) * per_cell <= PATCH_CACHE_BYTES
+            keep = self._patch_bytes + (hi - lo) * per_cell <= PATCH_CACHE_BYTES
             inten = torch.empty((hi - lo, img_dev.shape[0]), dtype=torch.float64, device=self.device)
             kept = {p: [] for p in panels}
             for a, b, batch, avg in self.patch_chunks(i, panels if keep else [], want_intensity=True):
@@ -250,8 +293,16 @@ class ImageProcessor(object):
                     kept[p].append(batch[p])
             self.patches.append({p: torch.cat(v) if v else torch.empty((0, len(self.parser.indices[p]), 40, 40), device=self.device)
                                  for p, v in kept.items()} if keep else None)
+            if keep:
+                self._patch_bytes += (hi - lo) * per_cell
             # preprocess.py:144-149,284-285: (avg_int + 1) / 2, all image channels, first applied panel
             self.intensity_full.append(self._gather_rows((inten + 1) / 2, tab.n, lo, hi).cpu().numpy())
+            img_bytes = img_dev.numel() * 4 + mask_dev.numel() * 4
+            self._resident.append(self._image_bytes + img_bytes <= IMAGE_CACHE_BYTES)
+            if self._resident[i]:
+                self._image_bytes += img_bytes
+            del img_dev, mask_dev
+            self.release(i)
 
     @staticmethod
     def _gather_rows(local, n_total, lo, hi):

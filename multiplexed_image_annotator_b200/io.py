@@ -252,10 +252,17 @@ def _read_any(path: str) -> np.ndarray:
             return a[0] if a.shape[0] == 1 else a                 # single page -> 2-D, as imread returns it
         except (ValueError, KeyError, struct.error):
             pass                                 # chunky RGB, exotic sample types ...: let PIL / OpenCV try
-        import cv2
-        ok, pages = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)
-        if ok and len(pages):
-            return np.stack(pages, 0) if len(pages) > 1 else pages[0]
+        try:
+            import cv2
+        except ImportError:
+            cv2 = None                           # no OpenCV: PIL below
+        if cv2 is not None:
+            ok, pages = cv2.imreadmulti(path, flags=cv2.IMREAD_UNCHANGED)
+            if ok and len(pages):
+                # OpenCV decodes colour pages as BGR(A); the reference reads through tifffile (RGB) and read_mask keeps
+                # channel 0 = red, so put the channels back in file order
+                pages = [pg[..., [2, 1, 0] + list(range(3, pg.shape[-1]))] if pg.ndim == 3 and pg.shape[-1] >= 3 else pg for pg in pages]
+                return np.stack(pages, 0) if len(pages) > 1 else pages[0]
     from PIL import Image
     im = Image.open(path)
     frames = []
@@ -296,9 +303,11 @@ class RunLog:
     FILE = "results/log.txt"
 
     def __init__(self, main_dir):
+        from .parallel import world
         os.makedirs(os.path.join(main_dir, "results"), exist_ok=True)
         self.log_file_path = os.path.join(main_dir, self.FILE)
-        self.log_file = open(self.log_file_path, "w", buffering=1)
+        # several ranks may share one main_dir (torchrun, one Annotator per rank): rank 0 owns the file
+        self.log_file = open(self.log_file_path if world()[0] == 0 else os.devnull, "w", buffering=1)
         self.log(f"Log file created at {time.ctime()}")
 
     def log(self, message):

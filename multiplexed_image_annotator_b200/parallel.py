@@ -78,3 +78,22 @@ def share_image_results(results: list, device) -> list:
             dist.broadcast(t, src)
         out.append((label, conf, counts))
     return out
+
+
+def is_writer() -> bool:
+    """Filesystem side effects (log, result CSVs / PNGs, tmp wipe) belong to rank 0 when several ranks share a main_dir."""
+    return world()[0] == 0
+
+
+def barrier() -> None:
+    if world()[1] > 1:
+        dist.barrier()
+
+
+def broadcast_object(obj, src: int = 0):
+    """Host object computed on `src` (e.g. the unseeded KMeans region labels) -> the same object on every rank."""
+    if world()[1] == 1:
+        return obj
+    box = [obj if world()[0] == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]

