@@ -74,13 +74,38 @@ def make_mm(mode):
         return f
     raise ValueError(mode)
 
+class PlanMM:
+    """Per-GEMM precision plan: `single` names the GEMMs run on plane 0 only (fp16 x fp16, one tensor pass,
+    half the L2 -> SM bytes); every other GEMM stays f16f8.  Names: embed, qkv, proj, fc1, fc2, optionally with a block range
+    suffix like fc1@0-5.  mode string: plan:qkv+fc1@6-11"""
+
+    def __init__(self, spec_str):
+        self.full, self.one = make_mm("f16f8:8"), make_mm("fp16x1")
+        self.rules = []
+        for item in filter(None, spec_str.split("+")):
+            name, _, rng = item.partition("@")
+            lo, hi = (int(v) for v in rng.split("-")) if rng else (0, 99)
+            self.rules.append((name, lo, hi))
+        self.block, self.name = -1, "embed"
+
+    def at(self, block, name):
+        self.block, self.name = block, name
+        return self
+
+    def __call__(self, a, w):
+        single = any(n == self.name and lo <= self.block <= hi for n, lo, hi in self.rules)
+        return (self.one if single else self.full)(a, w)
+
+
 def forward(x, sd, mm, head_w, head_b, attn_mode=None):
     B = x.shape[0]; D = spec.dim; H = spec.heads; hd = D // H
     p = spec.patch
     g = spec.img // p
     cols = x.reshape(B, spec.in_chans, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, -1)
     w = sd["patch_embed.proj.weight"].reshape(D, -1)
-    t = mm(cols, w.t()) + sd["patch_embed.proj.bias"]
+    named = isinstance(mm, PlanMM)
+    at = (lambda blk, name: mm.at(blk, name)) if named else (lambda blk, name: mm)
+    t = at(-1, "embed")(cols, w.t()) + sd["patch_embed.proj.bias"]
     t = t.reshape(B, g * g, D)
     t = torch.cat([sd["cls_token"].expand(B, -1, -1), t], 1) + sd["pos_embed"]
     N = t.shape[1]
@@ -88,16 +113,16 @@ def forward(x, sd, mm, head_w, head_b, attn_mode=None):
     for i in range(spec.depth):
         pre = f"blocks.{i}."
         h = F.layer_norm(t, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
-        qkv = mm(h.reshape(-1, D), sd[pre + "attn.qkv.weight"].t()) + sd[pre + "attn.qkv.bias"]
+        qkv = at(i, "qkv")(h.reshape(-1, D), sd[pre + "attn.qkv.weight"].t()) + sd[pre + "attn.qkv.bias"]
         qkv = qkv.reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         s = amm(q, k.transpose(-1, -2)) * hd ** -0.5
         pr = torch.softmax(s, -1)
         o = amm(pr, v).transpose(1, 2).reshape(B * N, D)
-        t = t + (mm(o, sd[pre + "attn.proj.weight"].t()) + sd[pre + "attn.proj.bias"]).reshape(B, N, D)
+        t = t + (at(i, "proj")(o, sd[pre + "attn.proj.weight"].t()) + sd[pre + "attn.proj.bias"]).reshape(B, N, D)
         h = F.layer_norm(t, (D,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-6)
-        u = F.gelu(mm(h.reshape(-1, D), sd[pre + "mlp.fc1.weight"].t()) + sd[pre + "mlp.fc1.bias"])
-        t = t + (mm(u, sd[pre + "mlp.fc2.weight"].t()) + sd[pre + "mlp.fc2.bias"]).reshape(B, N, D)
+        u = F.gelu(at(i, "fc1")(h.reshape(-1, D), sd[pre + "mlp.fc1.weight"].t()) + sd[pre + "mlp.fc1.bias"])
+        t = t + (at(i, "fc2")(u, sd[pre + "mlp.fc2.weight"].t()) + sd[pre + "mlp.fc2.bias"]).reshape(B, N, D)
     c = F.layer_norm(t[:, 0], (D,), sd["norm.weight"], sd["norm.bias"], 1e-6)
     return c @ head_w.t() + head_b
 
@@ -140,7 +165,7 @@ def run(mode, hw, hb, n=None, attn=None):
             for a in range(0, n or len(patches), 128):
                 outs.append(forward_folded(patches[a:a + 128], sd, mm, hw, hb, amm))
         return torch.cat(outs)
-    mm = make_mm(mode)
+    mm = PlanMM(mode[5:]) if mode.startswith("plan:") else make_mm(mode)
     amm = make_mm(attn) if attn else None
     outs = []
     with torch.no_grad():
