@@ -94,14 +94,27 @@ __device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t ct
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster.  Default semantics (as cutlass::arch::ClusterBarrier::
+// arrive): the explicit .release.cluster form compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which
+// was 9-32 % of the epilogue warps' stall samples (profiles/r02_gemm_epilogue.md).  What the arrive publishes here is "my
+// tcgen05.ld of this accumulator have completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it); no
+// global or shared write of this thread has to be visible to the MMA issuer.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+#ifdef RIBCA_ARRIVE_RELEASE_CLUSTER
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+#else
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -23,8 +23,8 @@ namespace ribca {
 
 typedef __nv_bfloat16 bf16;
 
-constexpr int kAttThreads = 256;
-// per warpgroup: Q, K, V x {hi, lo} tiles of TP rows x 128 B, + the O staging tile of the TMA store.
+constexpr int kAttThreads = 512;
+// per item group: Q, K, V x {hi, lo} tiles of TP rows x 128 B, + the O staging tile of the TMA store.
 // (the M = 128 MMA reads 128 Q rows: rows TP..127 fall into the K tile that follows - finite garbage
 // that only reaches S rows which are never used)
 __host__ __device__ constexpr int att_slot_bytes(int tp) { return 8 * tp * 128; }
@@ -60,30 +60,54 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
-__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <int TP>
+
+// Thread mapping.  The CTA holds two ITEM GROUPS of 256 threads; a group streams (cell, head) items through its own
+// shared-memory slot, 256 TMEM columns and mbarriers.  Inside a group TWO threads share a query row: warp w handles
+// TMEM lane quadrant w % 4 (the hardware rule for tcgen05.ld / st) and column half w / 4 - S columns [0, 64) or
+// [64, TP), O columns [0, HDP / 2) or [HDP / 2, HDP).  Half the per-thread instruction stream of the one-thread-per-row
+// form and twice the warps per scheduler: the kernel was bound by the latency of one warp's dependent softmax chain with
+// 2 warps per scheduler (issue 0.34, profiles/r01h_summary.md).  The two halves of a row exchange their maximum and
+// their sum through two spare TMEM columns of the group (tcgen05.st / ld), ordered by the group's named barrier.
+template <int TP, int HDP, int FMT>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_out, const AttnParams p, bf16* __restrict__ out_hi,
                     bf16* __restrict__ out_lo) {
+  static_assert(TP == 112 && HDP % 16 == 0 && HDP <= 64, "tile shape");
   constexpr int kKVBytes = TP * 128;
   constexpr int kQBytes = TP * 128;
   constexpr int kSlotBytes = att_slot_bytes(TP);
+  constexpr int kHalf0 = 64;                  // S columns of half 0; half 1 owns [64, TP)
+  constexpr int kOHalf = HDP / 2;             // O columns per half: 8, 16, 24 or 32
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSlotBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int wg = tid >> 7;                   // warpgroup = slot
-  const int row = tid & 127;                 // query row owned by this thread
-  const bool leader = row == 0;
-  uint64_t* bar_qk = bars + 4 * wg;          // TMA  -> S MMA
+  const int grp = tid >> 8;                  // item group = slot
+  const int gt = tid & 255;                  // thread within the group
+  const int half = gt >> 7;                  // column half
+  const int row = gt & 127;                  // query row owned by this thread (shared with the other half's thread)
+  const bool leader = gt == 0;
+  uint64_t* bar_qk = bars + 4 * grp;         // TMA  -> S MMA
   uint64_t* bar_v = bar_qk + 1;              // TMA  -> PV MMA
   uint64_t* bar_s = bar_qk + 2;              // S done  -> softmax, Q / K reload
   uint64_t* bar_o = bar_qk + 3;              // PV done -> output, V reload
@@ -100,10 +124,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-  const uint32_t tmem_sp = tmem_base + wg * 256;           // S (fp32, TP cols); later P_hi at +0, P_lo at +64 (bf16x2)
-  const uint32_t tmem_o = tmem_base + wg * 256 + 128;      // O (fp32, hdp cols)
+  const uint32_t tmem_sp = tmem_base + grp * 256;           // S (fp32, TP cols); later P_hi at +0, P_lo at +64 (bf16x2)
+  const uint32_t tmem_o = tmem_base + grp * 256 + 128;      // O (fp32, HDP cols)
+  const uint32_t tmem_x = tmem_base + grp * 256 + 192;      // exchange columns: max of half 0 / 1, sum of half 0 / 1
 
-  uint8_t* slot = smem + wg * kSlotBytes;
+  uint8_t* slot = smem + grp * kSlotBytes;
   uint8_t* q_s[2] = {slot, slot + kQBytes};
   uint8_t* k_s[2] = {slot + 2 * kQBytes, slot + 2 * kQBytes + kKVBytes};
   uint8_t* v_s[2] = {slot + 4 * kQBytes, slot + 4 * kQBytes + kKVBytes};
@@ -111,10 +136,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const bool tma_out = (p.hd % 8) == 0;      // rows of hd * 2 bytes must be multiples of 16 B for the bulk store
 
   const uint32_t idesc_s = make_instr_desc(128, TP, false);
-  const uint32_t idesc_o = make_instr_desc(128, p.hdp, true);
-  const int ksteps_s = p.hdp / 16;
+  const uint32_t idesc_o = make_instr_desc(128, HDP, true);
+  constexpr int ksteps_s = HDP / 16;
   const int n_items = p.cells * p.heads;
-  const int first = blockIdx.x * 2 + wg, stride = 2 * gridDim.x;
+  const int first = blockIdx.x * 2 + grp, stride = 2 * gridDim.x;
   const int my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
 
   auto load_qk = [&](int item) {
@@ -122,14 +147,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int row0 = cell * p.tokens;
     mbar_expect_tx(bar_qk, 2u * kQBytes + 2u * kKVBytes);
     for (int pl = 0; pl < 2; ++pl) {
-      tma_load_3d(q_s[pl], &tmap_q, bar_qk, head * p.hdp, row0, pl);
-      tma_load_3d(k_s[pl], &tmap_kv, bar_qk, (p.heads + head) * p.hdp, row0, pl);
+      tma_load_3d(q_s[pl], &tmap_q, bar_qk, head * HDP, row0, pl);
+      tma_load_3d(k_s[pl], &tmap_kv, bar_qk, (p.heads + head) * HDP, row0, pl);
     }
   };
   auto load_v = [&](int item) {
     const int cell = item / p.heads, head = item - cell * p.heads;
     mbar_expect_tx(bar_v, 2u * kKVBytes);
-    for (int pl = 0; pl < 2; ++pl) tma_load_3d(v_s[pl], &tmap_kv, bar_v, (2 * p.heads + head) * p.hdp, cell * p.tokens, pl);
+    for (int pl = 0; pl < 2; ++pl) tma_load_3d(v_s[pl], &tmap_kv, bar_v, (2 * p.heads + head) * HDP, cell * p.tokens, pl);
   };
 
   if (leader && my_items > 0) { load_qk(first); load_v(first); }
@@ -143,8 +168,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tcgen05_fence_after();
       const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};       // lo.hi, hi.lo, hi.hi
       uint32_t acc = 0;
+#pragma unroll
       for (int ps = 0; ps < 3; ++ps) {
         const uint32_t qa = smem_u32(q_s[pa[ps]]), kb = smem_u32(k_s[pb[ps]]);
+#pragma unroll
         for (int ks = 0; ks < ksteps_s; ++ks) {
           umma_bf16(tmem_sp, make_smem_desc(qa + ks * 32), make_smem_desc(kb + ks * 32), idesc_s, acc);
           acc = 1;
@@ -155,42 +182,65 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     mbar_wait(bar_s, ph);
     tcgen05_fence_after();
     if (leader && k + 1 < my_items) load_qk(item + stride);     // Q / K tiles are dead: prefetch the next item
-    // ---- softmax of this thread's row; P -> TMEM over S -----------------------------------------------
-    float s[TP];
+    // ---- softmax of this thread's half row; P -> TMEM over S ---------------------------------------------
+    // half 0: columns [0, 64) = 4 chunks of 16; half 1: columns [64, 112) = 3 chunks
+    constexpr int kMaxChunks = kHalf0 / 16;
+    const int n_chunks = half == 0 ? kHalf0 / 16 : (TP - kHalf0) / 16;
+    const int col0 = half * kHalf0;
+    float s[kMaxChunks * 16];
 #pragma unroll
-    for (int c = 0; c < TP / 16; ++c) tmem_ld16_nowait(tmem_sp + lane_addr + c * 16, reinterpret_cast<uint32_t*>(s) + c * 16);
+    for (int c = 0; c < kMaxChunks; ++c)
+      if (c < n_chunks) tmem_ld16_nowait(tmem_sp + lane_addr + col0 + c * 16, reinterpret_cast<uint32_t*>(s) + c * 16);
     tmem_ld_wait();
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < TP; ++j) {
-      if (j >= 96 && j >= p.tokens) s[j] = -INFINITY;         // only the tail chunk can be out of range (tokens > 96)
-      mx = fmaxf(mx, s[j]);
+    for (int c = 0; c < kMaxChunks; ++c) {
+      if (c < n_chunks) {
+        if (col0 + c * 16 + 16 > p.tokens) {                      // only a chunk that crosses `tokens` needs the mask
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + c * 16 + j >= p.tokens) s[c * 16 + j] = -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, s[c * 16 + j]);
+      }
     }
-    if (p.tokens <= 96) {                                       // generic (short sequences): mask everything
-#pragma unroll
-      for (int j = 0; j < TP; ++j) if (j >= p.tokens) s[j] = -INFINITY;
-      mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < TP; ++j) mx = fmaxf(mx, s[j]);
+    // exchange the half-row maxima (every row has at least its column 0 valid, so the joint maximum is finite)
+    tmem_st1(tmem_x + lane_addr + half, __float_as_uint(mx));
+    tmem_st_wait();
+    tcgen05_fence_before();
+    group_sync(grp);                       // also: every S value of the row is in registers before P overwrites S
+    tcgen05_fence_after();
+    {
+      uint32_t m0, m1;
+      tmem_ld2(tmem_x + lane_addr, m0, m1);
+      tmem_ld_wait();
+      mx = fmaxf(__uint_as_float(m0), __uint_as_float(m1));
     }
     const float off = mx * p.scale_log2e;
-    float sum = 0.f;
+    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < TP; ++j) {
-      s[j] = fast_exp2(fmaf(s[j], p.scale_log2e, -off));       // exp((s - max) / sqrt(hd)); 0 for masked columns
-      sum += s[j];
+    for (int c = 0; c < kMaxChunks; ++c) {
+      if (c < n_chunks) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          s[c * 16 + j] = fast_exp2(fmaf(s[c * 16 + j], p.scale_log2e, -off));       // exp((s - max) / sqrt(hd)); 0 for masked columns
+          s[c * 16 + j + 1] = fast_exp2(fmaf(s[c * 16 + j + 1], p.scale_log2e, -off));
+          sum0 += s[c * 16 + j];
+          sum1 += s[c * 16 + j + 1];
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16x2(s[c * 16 + 2 * e], s[c * 16 + 2 * e + 1], hi[e], lo[e]);
+        tmem_st8(tmem_sp + lane_addr + (col0 >> 1) + c * 8, hi);
+        tmem_st8(tmem_sp + lane_addr + 64 + (col0 >> 1) + c * 8, lo);
+      }
     }
-#pragma unroll
-    for (int c = 0; c < TP / 16; ++c) {
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_bf16x2(s[c * 16 + 2 * e], s[c * 16 + 2 * e + 1], hi[e], lo[e]);
-      tmem_st8(tmem_sp + lane_addr + c * 8, hi);
-      tmem_st8(tmem_sp + lane_addr + 64 + c * 8, lo);
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const float sum = sum0 + sum1;
+    tmem_st1(tmem_x + lane_addr + 2 + half, __float_as_uint(sum));
+    tmem_st_wait();
     tcgen05_fence_before();
-    wg_sync(wg);
+    group_sync(grp);
     // ---- O = P V --------------------------------------------------------------------------------------
     if (leader) {
       tcgen05_fence_after();
@@ -198,6 +248,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t pa[3] = {64, 0, 0};                      // P_lo, P_hi, P_hi
       const int pb[3] = {0, 1, 0};                            // V_hi, V_lo, V_hi
       uint32_t acc = 0;
+#pragma unroll
       for (int ps = 0; ps < 3; ++ps) {
         const uint32_t vb = smem_u32(v_s[pb[ps]]);
 #pragma unroll
@@ -211,37 +262,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     mbar_wait(bar_o, ph);
     tcgen05_fence_after();
     if (leader && k + 1 < my_items) load_v(item + stride);      // V tiles are dead
-    // ---- normalise, split, store ------------------------------------------------------------------------
+    // ---- normalise, split, store: this thread's O columns [half * kOHalf, +kOHalf) ----------------------------
     {
-      const float inv = 1.0f / sum;
-      const bool row_ok = row < p.tokens;
-      float o[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c * 16 < p.hdp) tmem_ld16_nowait(tmem_o + lane_addr + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
+      float o[kOHalf];
+      uint32_t x0, x1;
+      const uint32_t t_o = tmem_o + lane_addr + half * kOHalf;
+      if constexpr (kOHalf == 8) {
+        tmem_ld8_nowait(t_o, reinterpret_cast<uint32_t*>(o));
+      } else if constexpr (kOHalf == 16) {
+        tmem_ld16_nowait(t_o, reinterpret_cast<uint32_t*>(o));
+      } else if constexpr (kOHalf == 24) {
+        tmem_ld16_nowait(t_o, reinterpret_cast<uint32_t*>(o));
+        tmem_ld8_nowait(t_o + 16, reinterpret_cast<uint32_t*>(o) + 16);
+      } else {
+        tmem_ld16_nowait(t_o, reinterpret_cast<uint32_t*>(o));
+        tmem_ld16_nowait(t_o + 16, reinterpret_cast<uint32_t*>(o) + 16);
+      }
+      tmem_ld2(tmem_x + lane_addr + 2, x0, x1);
       tmem_ld_wait();
+      const float inv = 1.0f / (__uint_as_float(x0) + __uint_as_float(x1));     // fixed order: the same bits in both halves
+      const bool row_ok = row < p.tokens;
+      const int d0 = half * kOHalf;                                              // first head-dim column of this thread
       if (tma_out) {
         // the previous item's bulk store must have finished reading the staging tile
         if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        wg_sync(wg);
+        group_sync(grp);
         if (row_ok) {
           const int row_b = p.hd * 2;
           uint8_t* dh = o_s + row * row_b;
           uint8_t* dl = o_s + p.tokens * row_b + row * row_b;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            if (ch * 8 < p.hd) {
+          for (int ch = 0; ch < kOHalf / 8; ++ch) {
+            if (d0 + ch * 8 < p.hd) {
               uint32_t h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, p.out_fmt, h[e], l[e]);
-              *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+              for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, FMT, h[e], l[e]);
+              *reinterpret_cast<uint4*>(dh + (d0 + ch * 8) * 2) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(dl + (d0 + ch * 8) * 2) = make_uint4(l[0], l[1], l[2], l[3]);
             }
           }
         }
         fence_proxy_async_smem();
         tcgen05_fence_before();
-        wg_sync(wg);
+        group_sync(grp);
         if (leader) {
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                        ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * p.hd), "r"(cell * p.tokens), "r"(0)
@@ -252,22 +315,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const long long ob = ((long long)(cell * p.tokens + row)) * p.D + head * p.hd;
         if (row_ok) {
 #pragma unroll
-          for (int q4 = 0; q4 < 16; ++q4) {
-            const int d = q4 * 4;
+          for (int q4 = 0; q4 < kOHalf / 4; ++q4) {
+            const int d = d0 + q4 * 4;
             if (d < p.hd) {
               uint32_t h[2], l[2];
-              split_pair(o[d] * inv, o[d + 1] * inv, p.out_fmt, h[0], l[0]);
-              split_pair(o[d + 2] * inv, o[d + 3] * inv, p.out_fmt, h[1], l[1]);
+              split_pair(o[q4 * 4] * inv, o[q4 * 4 + 1] * inv, FMT, h[0], l[0]);
+              split_pair(o[q4 * 4 + 2] * inv, o[q4 * 4 + 3] * inv, FMT, h[1], l[1]);
               *reinterpret_cast<uint2*>(out_hi + ob + d) = make_uint2(h[0], h[1]);
               *reinterpret_cast<uint2*>(out_lo + ob + d) = make_uint2(l[0], l[1]);
             }
           }
         }
         tcgen05_fence_before();
-        wg_sync(wg);
+        group_sync(grp);
       }
     }
-    // (the barrier inside the output phase orders this warpgroup's TMEM reads before the next item's MMAs)
+    // (the barrier inside the output phase orders this group's TMEM reads before the next item's MMAs)
   }
   if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
@@ -294,18 +357,30 @@ static int make_qkv_map(CUtensorMap* map, const void* base, long long plane_elem
   return RIBCA_OK;
 }
 
-template <int TP>
+template <int TP, int HDP, int FMT>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const AttnParams& p, bf16* hi, bf16* lo,
                      cudaStream_t st) {
   constexpr int kAttSmemBytes = att_smem_bytes(TP);
-  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<TP>), (int)(kAttSmemBytes), "cudaFuncSetAttribute(attention_tc_kernel)"));
-  const int grid = std::min(p.cells * p.heads, num_sms());
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<TP, HDP, FMT>), (int)(kAttSmemBytes), "cudaFuncSetAttribute(attention_tc_kernel)"));
+  const int grid = std::min((p.cells * p.heads + 1) / 2, num_sms());
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)p.cells * p.heads * (double)p.tokens * p.tokens * p.hd, st);
-  attention_tc_kernel<TP><<<grid, kAttThreads, kAttSmemBytes, st>>>(mq, mkv, mo, p, hi, lo);
+  attention_tc_kernel<TP, HDP, FMT><<<grid, kAttThreads, kAttSmemBytes, st>>>(mq, mkv, mo, p, hi, lo);
   if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("attention_tc_kernel");
   return RIBCA_OK;
+}
+
+template <int TP, int FMT>
+static int launch_tc_hdp(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mo, const AttnParams& p, bf16* hi, bf16* lo,
+                         cudaStream_t st) {
+  switch (p.hdp) {
+    case 16: return launch_tc<TP, 16, FMT>(mq, mkv, mo, p, hi, lo, st);
+    case 32: return launch_tc<TP, 32, FMT>(mq, mkv, mo, p, hi, lo, st);
+    case 48: return launch_tc<TP, 48, FMT>(mq, mkv, mo, p, hi, lo, st);
+    case 64: return launch_tc<TP, 64, FMT>(mq, mkv, mo, p, hi, lo, st);
+    default: set_error("attention_tc: unsupported padded head_dim %d", p.hdp); return RIBCA_EUNSUPPORTED;
+  }
 }
 
 // qkv_split: [2][M][3*heads*hdp] bf16, plane stride qkv_plane elements; out_split [2][M][heads*hd]
@@ -339,7 +414,8 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
   }
   bf16* hi = static_cast<bf16*>(out_split);
   bf16* lo = hi + out_plane;
-  return launch_tc<TP>(mq, mkv, mo, p, hi, lo, st);
+  return out_fmt == kFmtF16F8 ? launch_tc_hdp<TP, kFmtF16F8>(mq, mkv, mo, p, hi, lo, st)
+                              : launch_tc_hdp<TP, kFmtBf16>(mq, mkv, mo, p, hi, lo, st);
 }
 
 }  // namespace ribca

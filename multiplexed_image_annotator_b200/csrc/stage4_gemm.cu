@@ -65,8 +65,15 @@ constexpr int kATile = BM * BK * 2;             // one plane of A:  16 KB at BK 
 constexpr int kABytes = 2 * kATile;             // both planes:    32 KB
 constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, both planes: 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kStagingTile = 4096;            // 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo tiles)
-constexpr int kStagingBytes = kStagingBufs * kStagingTile; // per epilogue warp
+#ifndef RIBCA_FORCE_CW16
+#define RIBCA_FORCE_CW16 0
+#endif
+#ifndef RIBCA_STAGING_BYTES
+#define RIBCA_STAGING_BYTES 4096
+#endif
+constexpr int kStagingBytes = RIBCA_STAGING_BYTES;   // per epilogue warp: 32 rows x 128 B (fp32 x 32 cols, or bf16 hi + lo tiles)
+constexpr int kStagingTile = kStagingBytes / kStagingBufs;   // 2 buffers: 16-column chunks (CW = 16), one store in flight per buffer
+static_assert(kStagingTile == 4096 || (kStagingTile == 2048 && RIBCA_FORCE_CW16), "a 2 KB staging tile holds 16-column chunks only");
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
 #ifndef RIBCA_OPERAND_L2_PROMOTION
@@ -545,7 +552,7 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   CUtensorMap map_a, map_w, map_out;
   RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
   RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN / 2, shp.n_planes));      // each CTA of a pair stages half of the W tile
-  epi.chunk = shp.BN % 32 == 0 ? 32 : 16;
+  epi.chunk = (shp.BN % 32 == 0 && !RIBCA_FORCE_CW16) ? 32 : 16;
   RIBCA_REQUIRE(!split_out || (out_plane * 2) % 16 == 0, "gemm: split output plane stride must be 16-byte aligned");
   RIBCA_TRY(make_output_map(&map_out, split_out, split_out ? out_split : (void*)out_f32, out_plane, M, N, epi.chunk));
   RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel), (int)(kSmemBytes), "cudaFuncSetAttribute(gemm_tcgen05_kernel)"));
