@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("RIBCA_PRECISION", "f16f8"))
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--interleave", action="store_true", help="two halves of every chunk on two streams (ribca_set_interleave; measured neutral, profiles/r02_interleave.md)")
+    ap.add_argument("--quick", action="store_true", help="iteration mode: no CPU baseline, annotator, strong or batch record")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2: 15-marker full panel -> vit_l (headline, BASELINE configs[1]); c3: 6-marker basic panel with "
                          "CD11c missing -> MAE imputer + vit_s (configs[2], secondary)")
@@ -61,7 +63,11 @@ def parse():
     ap.add_argument("--batch-images", type=int, default=64, help="images of the batch-CSV record (0 = skip)")
     ap.add_argument("--batch-size", type=int, default=2048)
     ap.add_argument("--no-annotator", action="store_true", help="skip the e2e_annotator leg")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_annotator = True
+        args.strong_size = args.batch_images = 0
+    return args
 
 
 def peaks():
@@ -272,6 +278,7 @@ def main():
         imputers = {panel: (mae, C3_PRESENT)}
     eng = engine.VitEngine(panel, sd, dev, precision=args.precision, max_cells_per_call=args.chunk)
     hp = HotPath({panel: index}, {panel: eng}, imputers, chunk_cells=args.chunk, device=dev, shard_cells=False)
+    ops.set_interleave(args.interleave)
     # head calibration: spread the label histogram of the random-init classifier.  Rank 0's statistics serve
     # every rank, so that all ranks hold the SAME model (the strong-scaling record shards one image over them).
     warm = hp.run(img_dev, mask_d, to_host=False, keep_probs=True)
@@ -331,11 +338,18 @@ def main():
 
     # ---- roofline of the dominant kernel, measured live with CUDA events around every launch -----------
     import ctypes as C
+    # (the profiled step runs the SERIAL schedule - the library switches the two-stream interleave off while profiling - so
+    #  every span holds one kernel alone; shares are quoted against that step's own time, `serial_step_ms`)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     L.ribca_profile_begin()
+    pe0.record()
     hp.run(img_dev, mask_d, to_host=False)
+    pe1.record()
     nc = 8
     ms = (C.c_double * nc)(); ln = (C.c_longlong * nc)(); wk = (C.c_double * nc)()
     _lib.check(L.ribca_profile_end(ms, ln, wk, nc), "ribca_profile_end")
+    torch.cuda.synchronize()
+    serial_step_ms = pe0.elapsed_time(pe1)
     pk, pk_src = peaks()
     # tensor time in units of one bf16 pass over K: bf16x3 = 3; f16f8 = fp16 pass + e4m3 pass over 2K at twice the rate = 2
     passes = {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1)
@@ -354,7 +368,9 @@ def main():
                 "frac": gemm_tf / peak_tf, "traffic": traffic, "l2": l2_note, "peak_source": pk_src + ", sustained bf16",
                 "launches_per_step": int(ln[0]), "avg_launch_ms": ms[0] / max(ln[0], 1), "kernel_ms_per_step": ms[0],
                 "algorithmic_flop_per_step": wk[0], "tensor_passes": passes, "issued_frac": passes * gemm_tf / peak_tf,
-                "share_of_step": ms[0] / (ms_res / args.steps),
+                "share_of_step": ms[0] / serial_step_ms, "serial_step_ms": serial_step_ms,
+                "schedule_note": "spans are measured on the serial schedule (one kernel at a time, like the ncu launch list); serial_step_ms is "
+                                 "that profiled step's own time (it carries the event overhead of ~700 spans)",
                 "note": "GEMM launches of the profiled step include the bf16x3 re-evaluation of the boundary cells (3 passes); "
                         "issued_frac counts them as the default precision's passes",
                 "other_kernels": {
@@ -469,6 +485,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": what + f"; CPU arms run a {sample_edge(args.steps, args.warmup)}^2 crop of the same scene",
                        "cells_per_gpu": n_cells, "chunk_cells": args.chunk, "precision": args.precision,
+                       "schedule": "two halves of every chunk interleaved on two streams (ribca_set_interleave)" if args.interleave else "serial: one stream, one kernel at a time",
                        "exact_labels": {"levels": hp.exact_labels, "eps": [exact.EPS1, exact.EPS2]},
                        "l2": f"inputs ({img_host.numel() * 2 / 1e6:.0f} MB image + {mask_host.numel() * 4 / 1e6:.0f} MB mask) exceed the 126 MB L2",
                        "parallelism": f"{world} x (one image per GPU), all-reduce of 18 counts"},

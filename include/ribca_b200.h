@@ -62,6 +62,14 @@ const char* ribca_last_error(void);
 int ribca_version(void);
 /* number of kernels this library has launched in the calling process (bench.py `gpu_launches`) */
 long long ribca_launch_count(void);
+/* Two-way interleave of ribca_vit_forward (opt-in: RIBCA_INTERLEAVE=1 in the environment or on = 1 here; measured
+ * neutral on the power-capped B200s of this pool, profiles/r02_interleave.md): the cells of one call are split in two halves that run the same kernel sequence on the caller's stream and on a
+ * library-owned side stream (fork / join by events, so the caller's stream ordering is unchanged).  The HBM-bound
+ * kernels of one half (LayerNorm, im2col, head) then share the SMs with the tensor-core GEMM of the other half, which
+ * leaves the registers and all but 224 KB of shared memory to them; every row is computed by the same kernels in the same
+ * order, so the probabilities are bit-identical to the serial schedule.  No reference counterpart (the reference runs
+ * one torch op at a time, cta/model.py:397-406). */
+int ribca_set_interleave(int on);
 
 /* Optional per-kernel-class device timing for roofline reports: between ribca_profile_begin() and
  * ribca_profile_end() every launch of the classes below is bracketed by CUDA events on its stream.

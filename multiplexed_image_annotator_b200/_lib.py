@@ -107,6 +107,7 @@ SIGNATURES = {
     "ribca_last_error": (C.c_char_p, []),
     "ribca_version": (_I, []),
     "ribca_launch_count": (_LL, []),
+    "ribca_set_interleave": (_I, [_I]),
     "ribca_profile_begin": (_I, []),
     "ribca_profile_end": (_I, [C.POINTER(_D), C.POINTER(_LL), C.POINTER(_D), _I]),
     "ribca_normalize_workspace_bytes": (_SZ, [_I, _I, _I]),

@@ -17,6 +17,9 @@ int ensure_dynamic_smem(const void* func, int bytes, const char* name);
 bool profiling();
 void prof_begin_span(int cls, double work, cudaStream_t st);
 void prof_end_span(cudaStream_t st);
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+bool interleave_enabled();                 // RIBCA_INTERLEAVE / ribca_set_interleave, off while profiling
+int side_stream(SideStream* out);          // this host thread's side stream on the current device (created on first use)
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {

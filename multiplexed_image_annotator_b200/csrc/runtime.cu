@@ -2,7 +2,9 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <stdlib.h>
 #include <set>
 #include <utility>
 #include <vector>
@@ -32,6 +34,37 @@ int ensure_dynamic_smem(const void* func, int bytes, const char* name) {
   if (done.count({func, dev})) return RIBCA_OK;
   RIBCA_TRY(check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), name));
   done.insert({func, dev});
+  return RIBCA_OK;
+}
+
+// ---- fork / join side stream of the two-way interleave (stage4_networks.cu) -----------------------------
+// One non-blocking side stream + two events per (host thread, device): a forward pass forks half of its cells onto the
+// side stream and joins back before it returns, so the caller's stream ordering is unchanged.
+static std::atomic<int> g_interleave{-1};      // -1 = read RIBCA_INTERLEAVE on first use
+
+bool interleave_enabled() {
+  int v = g_interleave.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("RIBCA_INTERLEAVE");
+    v = (e && e[0] == '1') ? 1 : 0;            // opt-in: no gain under the 1000 W power cap (profiles/r02_interleave.md)
+    g_interleave.store(v, std::memory_order_relaxed);
+  }
+  return v != 0 && !profiling();               // the per-kernel timing leg wants one kernel at a time
+}
+
+int side_stream(SideStream* out) {
+  static thread_local std::map<int, SideStream> per_device;
+  int dev = 0;
+  RIBCA_TRY(check_cuda(cudaGetDevice(&dev), "cudaGetDevice"));
+  auto it = per_device.find(dev);
+  if (it == per_device.end()) {
+    SideStream s{};
+    RIBCA_TRY(check_cuda(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags"));
+    RIBCA_TRY(check_cuda(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
+    RIBCA_TRY(check_cuda(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
+    it = per_device.emplace(dev, s).first;
+  }
+  *out = it->second;
   return RIBCA_OK;
 }
 
@@ -65,6 +98,11 @@ extern "C" {
 const char* ribca_last_error(void) { return ribca::g_err; }
 int ribca_version(void) { return 100; }
 long long ribca_launch_count(void) { return ribca::g_launches.load(std::memory_order_relaxed); }
+
+int ribca_set_interleave(int on) {
+  ribca::g_interleave.store(on ? 1 : 0, std::memory_order_relaxed);
+  return RIBCA_OK;
+}
 
 int ribca_profile_begin(void) {
   { std::lock_guard<std::mutex> lock(ribca::g_prof_mu); ribca::g_spans.clear(); }

@@ -80,7 +80,13 @@ constexpr int kTmemCols = 512;
 #define RIBCA_OPERAND_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B      // A/B-tested against 128B and NONE: no difference
 #endif
 // (register allocation is per 4 warps: 14 warps -> 16 x 32 x 128 registers; 18 warps would be capped at 96)
+// RIBCA_GEMM_MAXNREG=112 (a 12-byte spill) leaves room for two 256-thread LayerNorm blocks beside a resident GEMM CTA: the
+// co-residency experiment of profiles/r02_interleave.md; the default keeps the 154 registers of the unconstrained build
+#ifdef RIBCA_GEMM_MAXNREG
+#define RIBCA_GEMM_BOUNDS __maxnreg__(RIBCA_GEMM_MAXNREG)
+#else
 #define RIBCA_GEMM_BOUNDS __launch_bounds__(kGemmThreads, 1)
+#endif
 
 // shared-memory matrix descriptor of an operand tile whose rows are BK 16-bit elements
 __device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t smem_addr) {

@@ -58,8 +58,11 @@ im2col_split_kernel(const float* __restrict__ patches, int n_cells, int C, int f
 }
 
 // ---- LayerNorm -> split-bf16 ------------------------------------------------------------------
-// one warp per row, D % 4 == 0, D <= 1024; fp32 two-pass statistics
-__global__ void __launch_bounds__(256)
+// one warp per row, D % 4 == 0, D <= 1024; fp32 two-pass statistics.  NI = float4 per lane (ceil(D / 128)): the row lives
+// in 4 * NI registers, so that a 256-thread block stays under 48 registers per thread and two of them fit beside a
+// resident GEMM CTA (the two-stream interleave, ribca_set_interleave).
+template <int NI>
+__global__ void __launch_bounds__(256, 5)
 layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, int fmt, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
   const int lane = threadIdx.x & 31;
@@ -67,17 +70,17 @@ layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* _
   const int nv = D >> 2;                          // float4 per row
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
-    float4 v[8];
+    float4 v[NI];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nv) { v[i] = xr[idx]; sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
     }
     const float mean = warp_sum(sum) / (float)D;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nv) {
         const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
@@ -86,7 +89,7 @@ layernorm_split_kernel(const float* __restrict__ x, int M, int D, const float* _
     }
     const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nv) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
@@ -419,7 +422,13 @@ int layernorm_launch(const float* x, int M, int D, const float* g, const float* 
   bf16* hi = static_cast<bf16*>(out_split);
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_LAYERNORM, (double)M * (double)D * 8.0, st);
-  layernorm_split_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, M, D, g, b, eps, fmt, hi, hi + out_plane);
+  const int grid = grid_for(M, 8);
+  switch ((D / 4 + 31) / 32) {
+#define RIBCA_LN_CASE(NI) case NI: layernorm_split_kernel<NI><<<grid, 256, 0, st>>>(x, M, D, g, b, eps, fmt, hi, hi + out_plane); break;
+    RIBCA_LN_CASE(1) RIBCA_LN_CASE(2) RIBCA_LN_CASE(3) RIBCA_LN_CASE(4) RIBCA_LN_CASE(5) RIBCA_LN_CASE(6) RIBCA_LN_CASE(7)
+    default: layernorm_split_kernel<8><<<grid, 256, 0, st>>>(x, M, D, g, b, eps, fmt, hi, hi + out_plane); break;
+#undef RIBCA_LN_CASE
+  }
   if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("layernorm_split_kernel");
   return RIBCA_OK;
@@ -464,6 +473,8 @@ int attention_launch(const float* qkv, int cells, int tokens, int heads, int hd,
     default: set_error("attention: unsupported head_dim %d", hd); return RIBCA_EUNSUPPORTED;
   }
 }
+
+constexpr int kInterleaveMinCells = 512;   // below this the GEMMs are too short for a second stream to pay
 
 struct BlockBuffers {
   float* x;          // [M][D]
@@ -569,13 +580,48 @@ int ribca_attention(const float* qkv, int cells, int tokens, int heads, int head
   return attention_launch(qkv, cells, tokens, heads, head_dim, out_split, out_plane, format, as_stream(stream));
 }
 
+static int interleave_split(int n_cells);
+
+// the larger of the serial carve-up and the two-halves carve-up (they differ by alignment padding only)
 size_t ribca_vit_workspace_bytes(const ribca_vit_desc* desc, int n_cells) {
   if (!desc || n_cells <= 0) return 0;
   Carver cv{nullptr, 0};
   BlockBuffers b;
   block_buffers(cv, b, (long long)n_cells * desc->tokens, desc->dim, desc->heads);
-  return align_up(cv.off, 256);
+  size_t need = cv.off;
+  const int n0 = interleave_split(n_cells);
+  if (n0 > 0) {
+    Carver c2{nullptr, 0};
+    block_buffers(c2, b, (long long)n0 * desc->tokens, desc->dim, desc->heads);
+    block_buffers(c2, b, (long long)(n_cells - n0) * desc->tokens, desc->dim, desc->heads);
+    need = std::max(need, c2.off);
+  }
+  return align_up(need, 256);
 }
+
+// one contiguous range of cells through the classifier on one stream (buffers carved by the caller)
+static int vit_forward_range(const ribca_vit_desc* desc, const float* wf32, const bf16* wsplit, const float* patches,
+                             int n_cells, float* probs, float* logits, const BlockBuffers& b, int precision, cudaStream_t st) {
+  const int D = desc->dim, T = desc->tokens, C = desc->in_chans;
+  const long long M = (long long)n_cells * T;
+  // patch embedding: im2col into the (larger) MLP buffer, GEMM with the cls/pos/bias row table
+  const int Kpe = 16 * C;
+  const long long pe_plane = M * Kpe;
+  const int fmt = fmt_of(precision), wls = desc->w_log2_scale;
+  im2col_split_kernel<<<grid_for((long long)n_cells * C * 400, 256), 256, 0, st>>>(patches, n_cells, C, fmt, b.h, b.h + pe_plane);
+  RIBCA_LAUNCH_CHECK("im2col_split_kernel");
+  RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
+                        wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, wls, st));
+  float* x_cls = nullptr;
+  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st, &x_cls));
+  head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x_cls, n_cells, 1, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
+                                                         wf32 + desc->head_w, wf32 + desc->head_b, desc->classes, probs, logits);
+  RIBCA_LAUNCH_CHECK("head_softmax_kernel");
+  return RIBCA_OK;
+}
+
+// cells of the first half of a two-way interleaved call (0 = run the call as one range)
+static int interleave_split(int n_cells) { return n_cells >= kInterleaveMinCells ? (n_cells + 1) / 2 : 0; }
 
 int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void* wsplit_, const float* patches,
                       int n_cells, float* probs, float* logits, void* workspace, size_t workspace_bytes,
@@ -591,34 +637,43 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
   }
   cudaStream_t st = as_stream(stream);
   const bf16* wsplit = static_cast<const bf16*>(wsplit_);
-  const int D = desc->dim, T = desc->tokens, C = desc->in_chans;
+  const int D = desc->dim, T = desc->tokens;
   const long long M = (long long)n_cells * T;
   RIBCA_REQUIRE(M < (1ll << 31) / 16, "ribca_vit_forward: %d cells per call is too many; chunk the batch", n_cells);
   Carver cv{static_cast<char*>(workspace), 0};
-  BlockBuffers b;
-  block_buffers(cv, b, M, D, desc->heads);
   if (precision == RIBCA_FP32) {          // the reference's own arithmetic on the FP32 pipe (stage4_fp32.cu)
     RIBCA_REQUIRE(desc->plane_format == RIBCA_PLANES_F32, "ribca_vit_forward: RIBCA_FP32 needs fp32 weight matrices (plane format %d given)",
                   desc->plane_format);
+    BlockBuffers b;
+    block_buffers(cv, b, M, D, desc->heads);
     return vit_forward_f32(desc, wf32, static_cast<const float*>(wsplit_), patches, n_cells, probs, logits, b.x,
                            reinterpret_cast<float*>(b.a), b.qkv, reinterpret_cast<float*>(b.h), st);
   }
-  // patch embedding: im2col into the (larger) MLP buffer, GEMM with the cls/pos/bias row table
-  const int Kpe = 16 * C;
-  const long long pe_plane = M * Kpe;
-  const int fmt = fmt_of(precision), wls = desc->w_log2_scale;
-  RIBCA_REQUIRE(desc->plane_format == fmt, "ribca_vit_forward: weights are packed in plane format %d but precision %d needs %d",
-                desc->plane_format, precision, fmt);
-  im2col_split_kernel<<<grid_for((long long)n_cells * C * 400, 256), 256, 0, st>>>(patches, n_cells, C, fmt, b.h, b.h + pe_plane);
-  RIBCA_LAUNCH_CHECK("im2col_split_kernel");
-  RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
-                        wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, wls, st));
-  float* x_cls = nullptr;
-  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st, &x_cls));
-  head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x_cls, n_cells, 1, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
-                                                         wf32 + desc->head_w, wf32 + desc->head_b, desc->classes, probs, logits);
-  RIBCA_LAUNCH_CHECK("head_softmax_kernel");
-  return RIBCA_OK;
+  RIBCA_REQUIRE(desc->plane_format == fmt_of(precision), "ribca_vit_forward: weights are packed in plane format %d but precision %d needs %d",
+                desc->plane_format, precision, fmt_of(precision));
+  const int n0 = interleave_enabled() ? interleave_split(n_cells) : 0;
+  if (n0 == 0) {
+    BlockBuffers b;
+    block_buffers(cv, b, M, D, desc->heads);
+    return vit_forward_range(desc, wf32, wsplit, patches, n_cells, probs, logits, b, precision, st);
+  }
+  // two-way interleave: half 0 on the caller's stream, half 1 on the side stream (include/ribca_b200.h: ribca_set_interleave)
+  const int n1 = n_cells - n0;
+  BlockBuffers b0, b1;
+  block_buffers(cv, b0, (long long)n0 * T, D, desc->heads);
+  block_buffers(cv, b1, (long long)n1 * T, D, desc->heads);
+  SideStream side;
+  RIBCA_TRY(side_stream(&side));
+  RIBCA_TRY(check_cuda(cudaEventRecord(side.fork, st), "cudaEventRecord(fork)"));
+  RIBCA_TRY(check_cuda(cudaStreamWaitEvent(side.stream, side.fork, 0), "cudaStreamWaitEvent(fork)"));
+  const long long per_cell = (long long)desc->in_chans * 1600;
+  const int rc1 = vit_forward_range(desc, wf32, wsplit, patches + n0 * per_cell, n1, probs + (long long)n0 * desc->classes,
+                                    logits ? logits + (long long)n0 * desc->classes : nullptr, b1, precision, side.stream);
+  const int rc0 = vit_forward_range(desc, wf32, wsplit, patches, n0, probs, logits, b0, precision, st);
+  // always join, also after a failed launch: the caller's stream must not run ahead of the side stream
+  const int rcj = check_cuda(cudaEventRecord(side.join, side.stream), "cudaEventRecord(join)");
+  const int rcw = rcj == RIBCA_OK ? check_cuda(cudaStreamWaitEvent(st, side.join, 0), "cudaStreamWaitEvent(join)") : rcj;
+  return rc1 != RIBCA_OK ? rc1 : rc0 != RIBCA_OK ? rc0 : rcw;
 }
 
 static void mae_carve(const ribca_mae_desc* d, int n_cells, int n_present, Carver& cv, BlockBuffers& be, BlockBuffers& bd,

@@ -56,6 +56,13 @@ def launch_count() -> int:
     return int(_lib.lib().ribca_launch_count())
 
 
+def set_interleave(on: bool) -> None:
+    """Two-way interleave of the classifier forward (ribca_set_interleave): halves of a call on two streams, so the HBM-bound
+    LayerNorm / im2col kernels of one half run under the tensor-core GEMM of the other.  Opt-in (neutral under the
+    power cap, profiles/r02_interleave.md); bit-identical results."""
+    _lib.check(_lib.lib().ribca_set_interleave(1 if on else 0), "ribca_set_interleave")
+
+
 # ------------------------------------------------------------------------------------------------
 # host-side plans
 # ------------------------------------------------------------------------------------------------

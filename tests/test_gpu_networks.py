@@ -245,6 +245,27 @@ def test_engine_packs_every_precision_on_demand():
         eng.forward(x, precision="fp8")
 
 
+@pytest.mark.parametrize("n", [512, 777, 1300])
+def test_vit_interleaved_halves_are_bit_identical_to_the_serial_schedule(n):
+    """ribca_set_interleave: a call of >= 512 cells is split in two halves on two streams (LayerNorm of one half under the
+    GEMM of the other).  Every row goes through the same kernels, so the probabilities must carry the same bits; the
+    work queued on the caller's stream after the call must see the side stream's results (join)."""
+    sd, _ = _vit_pair("immune_base", seed=5)
+    eng = engine.VitEngine("immune_base", sd, DEV)
+    x = torch.randn((n, 7, 40, 40), device=DEV, generator=torch.Generator(device=DEV).manual_seed(n))
+    try:
+        ops.set_interleave(False)
+        serial, serial_logits = eng.forward(x, return_logits=True)
+        ops.set_interleave(True)
+        for _ in range(3):
+            both, both_logits = eng.forward(x, return_logits=True)
+            total = both.sum(1)                                  # consumer on the caller's stream right after the join
+            assert torch.equal(both, serial) and torch.equal(both_logits, serial_logits)
+            assert torch.allclose(total, torch.ones_like(total), atol=1e-5)
+    finally:
+        ops.set_interleave(False)
+
+
 @pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 @pytest.mark.parametrize("panel", ["immune_base", "immune_extended", "immune_full", "structure", "nerve_cell"])
 def test_vit_vs_oracle_on_real_patches(panel, precision):
