@@ -63,7 +63,11 @@ def parse():
     ap.add_argument("--batch-images", type=int, default=64, help="images of the batch-CSV record (0 = skip)")
     ap.add_argument("--batch-size", type=int, default=2048)
     ap.add_argument("--no-annotator", action="store_true", help="skip the e2e_annotator leg")
+    ap.add_argument("--ln-fold", type=int, default=None, help="A/B: RIBCA_LN_FOLD mask (0 = separate LayerNorm kernels [default], 1 = norm1 folded into "
+                                                              "qkv, 3 = norm1 and norm2 folded; profiles/r02_lnfold.md)")
     args = ap.parse_args()
+    if args.ln_fold is not None:
+        os.environ["RIBCA_LN_FOLD"] = str(args.ln_fold)
     if args.quick:
         args.no_cpu_baseline = args.no_annotator = True
         args.strong_size = args.batch_images = 0

@@ -193,11 +193,37 @@ int ribca_build_patches_resized(const float* img, const int32_t* mask, int C_img
  *     RIBCA_EPI_GELU        out split-bf16 {hi, lo}[row*N+col] = gelu_erf(v), plane stride out_plane
  *     RIBCA_EPI_STORE_SPLIT out split-bf16 {hi, lo}[row*N+col] = v
  */
-enum ribca_epilogue { RIBCA_EPI_STORE = 0, RIBCA_EPI_RESIDUAL = 1, RIBCA_EPI_GELU = 2, RIBCA_EPI_STORE_SPLIT = 3 };
+enum ribca_epilogue { RIBCA_EPI_STORE = 0, RIBCA_EPI_RESIDUAL = 1, RIBCA_EPI_GELU = 2, RIBCA_EPI_STORE_SPLIT = 3,
+                      RIBCA_EPI_STORE_LN = 4, RIBCA_EPI_RESIDUAL_LN = 5 /* ribca_gemm_ln only */ };
 int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long long w_plane,
                          int M, int N, int K, const float* bias, const float* row_table,
                          int table_period, int epilogue, float* out_f32, void* out_split,
                          long long out_plane, int precision, int w_log2_scale, ribca_stream_t stream);
+/* LayerNorm folded into the GEMMs around it (timm Block: x + attn(norm1(x)), x + mlp(norm2(x)), cta/model.py:54-55), so that
+ * no LayerNorm kernel reads the residual stream:
+ *   producer (RIBCA_EPI_STORE_LN / RIBCA_EPI_RESIDUAL_LN: patch embedding, proj, fc2): stores the fp32 rows (out_f32 = v or
+ *     out_f32 += v) and, from the same values, their operand planes (out_split, plane stride out_plane, in the format of
+ *     `precision`) and per-row partial sums ln->stats_out[row][slot] = (sum, sum of squares) over the columns of that slot;
+ *     ribca_gemm_ln_slots(N, precision) slots are filled, the partition of columns over slots is fixed (bit-reproducible);
+ *   consumer (ln->stats_in != NULL; qkv, fc1): A = the planes of the RAW rows, W' = W * diag(gamma) packed as usual,
+ *     ln->c1[n] = sum_k W'[n][k], bias[n] = c2[n] = b[n] + sum_k beta[k] W[n][k];  with mean / rstd of the row from the
+ *     statistics over K elements:  v = rstd * (acc - mean * c1[col]) + c2[col]  ( = LayerNorm(x) . W^T + b ), then the
+ *     epilogue proper (RIBCA_EPI_STORE / GELU / STORE_SPLIT).
+ * ln == NULL: exactly ribca_gemm_splitbf16. */
+#define RIBCA_LN_SLOTS 8
+typedef struct ribca_ln_fold {
+  const float* stats_in;   /* [M][RIBCA_LN_SLOTS][2] or NULL */
+  const float* c1;         /* [N] (stats_in != NULL) */
+  int slots_in;            /* filled slots of stats_in */
+  float eps;               /* LayerNorm epsilon */
+  float* stats_out;        /* [M][RIBCA_LN_SLOTS][2] (the *_LN epilogues) */
+} ribca_ln_fold;
+int ribca_gemm_ln(const void* A, long long a_plane, const void* W, long long w_plane,
+                  int M, int N, int K, const float* bias, const float* row_table,
+                  int table_period, int epilogue, float* out_f32, void* out_split,
+                  long long out_plane, int precision, int w_log2_scale, const ribca_ln_fold* ln,
+                  ribca_stream_t stream);
+int ribca_gemm_ln_slots(int N, int precision);
 /* With precision RIBCA_F16F8 the operands are RIBCA_PLANES_F16F8 planes: plane 0 = fp16, plane 1 = two
  * e4m3 per element; W is packed in the W role with scale 2^t (ribca_split_planes) and w_log2_scale = t + 8
  * (the accumulator is multiplied by 2^-w_log2_scale).  A RIBCA_EPI_GELU output is written in the same
@@ -231,6 +257,9 @@ typedef struct ribca_block_desc {
   long long ln1_g, ln1_b, ln2_g, ln2_b;           /* wf32 */
   long long qkv_b, proj_b, fc1_b, fc2_b;           /* wf32 */
   long long qkv_w, proj_w, fc1_w, fc2_w;           /* wsplit */
+  /* LayerNorm-folded packing (ribca_vit_desc.ln_folded): qkv_w / fc1_w hold W * diag(gamma); wf32 vectors
+   * c1[n] = sum_k (W gamma)[n][k] and c2[n] = b[n] + sum_k beta[k] W[n][k] (qkv ones head-padded like qkv_b) */
+  long long qkv_c1, qkv_c2, fc1_c1, fc1_c2;
 } ribca_block_desc;
 /* qkv_w / qkv_b are stored head-padded: [3][heads][hdp][D] and [3][heads][hdp] with hdp = head_dim
  * rounded up to a multiple of 16 and zero rows in the padding (hdp == head_dim for 32 / 48 / 64). */
@@ -239,6 +268,9 @@ typedef struct ribca_vit_desc {
   int dim, heads, depth, in_chans, classes, tokens;  /* tokens = 101 */
   int plane_format;                                  /* ribca_plane_format of wsplit */
   int w_log2_scale;                                  /* RIBCA_PLANES_F16F8: t + 8 (weights packed with scale 2^t) */
+  int ln_folded;                                     /* bit 0: norm1 is folded into qkv (qkv_w packed as W diag(gamma), qkv_c1 / qkv_c2 valid), bit 1:
+                                                        norm2 into fc1 (ribca_ln_fold); tensor-core formats only */
+  int reserved;
   long long split_plane;                             /* elements between the hi and lo plane */
   long long embed_w;                                 /* wsplit [dim][16*in_chans] */
   long long embed_table;                             /* wf32 [tokens][dim]: row0 = cls+pos0, row t = bias+pos_t */

@@ -75,15 +75,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+class LnFold(C.Structure):
+    _fields_ = [("stats_in", C.c_void_p), ("c1", C.c_void_p), ("slots_in", C.c_int), ("eps", C.c_float), ("stats_out", C.c_void_p)]
+
+
+LN_SLOTS = 8
+
+
 class BlockDesc(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_b", "proj_b", "fc1_b", "fc2_b",
-                                             "qkv_w", "proj_w", "fc1_w", "fc2_w")]
+                                             "qkv_w", "proj_w", "fc1_w", "fc2_w", "qkv_c1", "qkv_c2", "fc1_c1", "fc1_c2")]
 
 
 class VitDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("heads", C.c_int), ("depth", C.c_int), ("in_chans", C.c_int),
                 ("classes", C.c_int), ("tokens", C.c_int), ("plane_format", C.c_int), ("w_log2_scale", C.c_int),
-                ("split_plane", C.c_longlong),
+                ("ln_folded", C.c_int), ("reserved", C.c_int), ("split_plane", C.c_longlong),
                 ("embed_w", C.c_longlong), ("embed_table", C.c_longlong), ("norm_g", C.c_longlong),
                 ("norm_b", C.c_longlong), ("head_w", C.c_longlong), ("head_b", C.c_longlong),
                 ("blocks", BlockDesc * 16)]
@@ -123,6 +130,8 @@ SIGNATURES = {
     "ribca_build_patches_resized": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I),
                                          C.POINTER(_P), C.POINTER(_D), _I, C.POINTER(_I), C.POINTER(_D), _I, _P, _P, _P]),
     "ribca_gemm_splitbf16": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _P, _I, _I, _P, _P, _LL, _I, _I, _P]),
+    "ribca_gemm_ln": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _P, _I, _I, _P, _P, _LL, _I, _I, C.POINTER(LnFold), _P]),
+    "ribca_gemm_ln_slots": (_I, [_I, _I]),
     "ribca_split_bf16": (_I, [_P, _LL, _P, _P, _P]),
     "ribca_split_planes": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
     "ribca_layernorm_split": (_I, [_P, _I, _I, _P, _P, _F, _P, _LL, _I, _P]),

@@ -104,7 +104,40 @@ struct GemmEpilogue {
   __nv_bfloat16* out_lo;
   int out_fmt;              // plane format of a split output (kFmtBf16 / kFmtF16F8)
   float acc_scale;          // accumulator scale (2^-(t+8) for f16f8 weights, else 1)
+  // LayerNorm folded into this GEMM (include/ribca_b200.h: ribca_ln_fold)
+  const float* stats_in;    // [M][kLnSlots][2] partial (sum, sum of squares) of the rows the A planes were split from, or null
+  const float* c1;          // [N] sum_k W'[n][k] (stats_in != null); `bias` then holds c2
+  int slots_in;             // filled slots of stats_in
+  float inv_dim, ln_eps;    // 1 / D of the normalised rows, LayerNorm epsilon
+  float* stats_out;         // *_LN epilogues: [M][kLnSlots][2] partial statistics of the stored fp32 rows
 };
+constexpr int kLnSlots = RIBCA_LN_SLOTS;
+
+// mean and 1 / sqrt(var + eps) of one row from its partial sums (fixed slot order: the same bits on every schedule)
+// the row's 8 slots are one 64-byte line: four independent 16-byte loads (one memory latency) ...
+__device__ __forceinline__ void ln_stats_request(const float* __restrict__ stats, long long row, int M, float4 (&q)[kLnSlots / 2]) {
+  const float4* p = reinterpret_cast<const float4*>(stats) + row * (kLnSlots / 2);
+#pragma unroll
+  for (int i = 0; i < kLnSlots / 2; ++i) q[i] = row < M ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// ... then the fixed-order sum over the filled slots: mean and 1 / sqrt(var + eps) (the same bits on every schedule)
+__device__ __forceinline__ void ln_stats_finish(const float4 (&q)[kLnSlots / 2], int slots, float inv_dim, float eps, float& mean, float& rstd) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnSlots / 2; ++i) {
+    if (2 * i < slots) { s1 += q[i].x; s2 += q[i].y; }
+    if (2 * i + 1 < slots) { s1 += q[i].z; s2 += q[i].w; }
+  }
+  mean = s1 * inv_dim;
+  const float var = fmaxf(fmaf(-mean, mean, s2 * inv_dim), 0.f);
+  rstd = 1.0f / sqrtf(var + eps);
+}
+__device__ __forceinline__ void ln_row_stats(const float* __restrict__ stats, long long row, int slots, float inv_dim, float eps,
+                                             float& mean, float& rstd) {
+  float4 q[kLnSlots / 2];
+  ln_stats_request(stats, row, 0x7fffffff, q);
+  ln_stats_finish(q, slots, inv_dim, eps, mean, rstd);
+}
 
 struct GemmShape {
   int M, N, K;
@@ -145,6 +178,19 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   int stg_sel = 0;
   const bool split_out = epi.mode == RIBCA_EPI_GELU || epi.mode == RIBCA_EPI_STORE_SPLIT;
   const int n_chunks = BN / CW;
+  // folded LayerNorm: bv[0..3] = c1, bv[4..7] = c2 of 16 columns, requested half a chunk (or a tile) ahead
+  float4 bv[8];
+  bool c_ready = false;
+  auto load_c = [&](int colx) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      bv[q] = __ldg(reinterpret_cast<const float4*>(epi.c1 + colx) + q);
+      bv[4 + q] = __ldg(reinterpret_cast<const float4*>(epi.bias + colx) + q);
+    }
+  };
+  float4 ln_q[kLnSlots / 2];
+  if (epi.stats_in && (int)(blockIdx.x >> 1) < n_pairs)
+    ln_stats_request(epi.stats_in, (2 * ((int)(blockIdx.x >> 1) / n_tiles_n) + cta_rank) * BM + quad * 32 + lane, shp.M, ln_q);
   int local = 0;
   for (int pr = blockIdx.x >> 1; pr < n_pairs; pr += gridDim.x >> 1, ++local) {
     const int buf = local & 1;
@@ -152,6 +198,18 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
     const int m0 = (2 * (pr / n_tiles_n) + cta_rank) * BM, n0 = (pr % n_tiles_n) * BN;
     const int row = m0 + quad * 32 + lane;
     const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
+    // folded LayerNorm of the A rows: v = rstd * (acc * sc - mean * c1[col]) + c2[col]  ->  fma(acc, rs, fma(-mr, c1, c2))
+    float ln_rs = 0.f, ln_mr = 0.f;
+    if (epi.stats_in) {
+      // this tile's row statistics were requested one tile ahead (a 64-byte line per row from a 26 MB table: a DRAM latency
+      // that would otherwise sit in front of every tile); request the next tile's now
+      float mean, rstd;
+      ln_stats_finish(ln_q, epi.slots_in, epi.inv_dim, epi.ln_eps, mean, rstd);
+      ln_rs = rstd * epi.acc_scale;
+      ln_mr = mean * rstd;
+      const int pn = pr + (gridDim.x >> 1);
+      if (pn < n_pairs) ln_stats_request(epi.stats_in, (2 * (pn / n_tiles_n) + cta_rank) * BM + quad * 32 + lane, shp.M, ln_q);
+    }
     mbar_wait(&tmem_full[buf], use & 1u);
     tcgen05_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
@@ -169,8 +227,9 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
 #pragma unroll
       for (int q = 0; q < CW / 16; ++q) tmem_ld16_nowait(t_row + (uint32_t)(c + 16 * q), reinterpret_cast<uint32_t*>(v) + 16 * q);
       // bias of this chunk: requested while the TMEM loads are in flight
-      float4 bv[CW / 4];
-      if (epi.bias) {
+      if (epi.stats_in) {
+        if (!c_ready) load_c(col);
+      } else if (epi.bias) {
 #pragma unroll
         for (int q = 0; q < CW / 4; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q);
       }
@@ -180,7 +239,26 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
 #pragma unroll
       for (int hh = 0; hh < CW / 16; ++hh) {
         float* u = v + 16 * hh;
-        if (epi.bias) {
+        if (epi.stats_in) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 a = bv[q], b = bv[4 + q];
+            u[4 * q] = fmaf(u[4 * q], ln_rs, fmaf(-ln_mr, a.x, b.x)); u[4 * q + 1] = fmaf(u[4 * q + 1], ln_rs, fmaf(-ln_mr, a.y, b.y));
+            u[4 * q + 2] = fmaf(u[4 * q + 2], ln_rs, fmaf(-ln_mr, a.z, b.z)); u[4 * q + 3] = fmaf(u[4 * q + 3], ln_rs, fmaf(-ln_mr, a.w, b.w));
+          }
+          // the vectors of the NEXT 16 columns (this chunk's second half, or the next chunk of the tile) are requested now: the
+          // loads miss L1 (224 KB of it is shared memory) and used to sit on the long scoreboard in front of every half
+          if (hh + 1 < CW / 16) load_c(col + 16 * (hh + 1));
+          else if (j + kEpiPerQuad < n_chunks) { load_c(n0 + (j + kEpiPerQuad) * CW); c_ready = true; }
+          else {
+            // first chunk of this warp in the CTA's next tile (its start warp rotates with `local`)
+            const int pn = pr + (gridDim.x >> 1);
+            int jn = sub + (local + 1) % kEpiPerQuad;
+            if (jn >= kEpiPerQuad) jn -= kEpiPerQuad;
+            c_ready = pn < n_pairs && jn < n_chunks;
+            if (c_ready) load_c((pn % n_tiles_n) * BN + jn * CW);
+          }
+        } else if (epi.bias) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b = bv[4 * hh + q];
@@ -267,9 +345,166 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap& tmap_out, const
   __syncwarp();
 }
 
+
+// ---- *_LN epilogues: the fp32 row store of a residual / embedding GEMM that ALSO leaves what the next LayerNorm-folded
+// GEMM reads: the operand planes of the new rows and per-row partial sums (sum, sum of squares).  x_new = x_old + (acc * sc
+// + bias) is computed in the SM, so memory holds exactly the value the planes and the statistics come from.  16-column
+// chunks; the warp's 4 KB staging area is split in a 2 KB fp32 tile (32 rows x 64 B) and a 2 KB plane tile (hi, lo: 32 rows x
+// 32 B each).  x_old / x_new move between global memory and the fp32 tile with COALESCED 16-byte accesses (lane l: row l / 4 +
+// 8 i, 16-byte piece l % 4: 64-byte row segments, 8 rows per instruction) and between the tile and the row-per-lane
+// accumulator layout through shared memory: row-per-lane global accesses (32 lines per instruction) were 73 % of the
+// epilogue's stall samples (profiles/r02_lnfold.md).  x_old of the next chunk is requested one chunk ahead; the planes
+// leave by TMA like every 16-bit output.  The two warps of a lane quadrant take the even / odd chunks in ascending order and
+// own one statistics slot each: slot = (n0 / BN) * 2 + sub, so the partial sums do not depend on the schedule.
+__device__ __forceinline__ void epilogue_loop_ln(const CUtensorMap& tmap_planes, const GemmShape& shp, const GemmEpilogue& epi,
+                                                 uint8_t* staging_base, uint32_t tmem_base, uint64_t* tmem_full,
+                                                 uint64_t* tmem_empty, int warp, int lane) {
+  static_assert(kStagingBufs == 1 && kEpiPerQuad == 2 && kStagingBytes >= 4096, "one 4 KB staging area per warp; 2 warps per quadrant");
+  constexpr int CW = 16;
+  const int BN = shp.BN;
+  const int n_tiles_n = shp.N / BN;
+  const int n_pairs = (((shp.M + BM - 1) / BM + 1) / 2) * n_tiles_n;
+  const int cta_rank = (int)cluster_ctarank();
+  const int quad = warp & 3;
+  const int sub = (warp - 2) >> 2;
+  uint8_t* xs = staging_base + (warp - 2) * kStagingBytes;          // fp32 tile, rows of 64 B, 16-byte pieces XOR-swizzled
+  uint8_t* ps = xs + 2048;                                          // plane tiles (TMA store source, SWIZZLE_32B)
+  const uint32_t ps_addr = smem_u32(ps);
+  const bool resid = epi.mode == RIBCA_EPI_RESIDUAL_LN;
+  const int n_chunks = BN / CW;
+  const float sc = epi.acc_scale;
+  // row-per-lane view of the fp32 tile: lane = row, piece ch at ((ch ^ ((lane >> 1) & 3)) << 4)
+  const int rp_base = lane * 64, rp_x = (lane >> 1) & 3;
+  // coalesced view: piece l % 4 of rows l / 4 + 8 i
+  const int co_piece = lane & 3, co_row = lane >> 2;
+  int local = 0;
+  for (int pr = blockIdx.x >> 1; pr < n_pairs; pr += gridDim.x >> 1, ++local) {
+    const int buf = local & 1;
+    const uint32_t use = (uint32_t)(local >> 1);
+    const int m0 = (2 * (pr / n_tiles_n) + cta_rank) * BM, n0 = (pr % n_tiles_n) * BN;
+    const int r0 = m0 + quad * 32;
+    const int row = r0 + lane;
+    const bool row_ok = row < shp.M;
+    const float* table_row = epi.row_table ? epi.row_table + (long long)(row % epi.table_period) * shp.N : nullptr;
+    float4 xg[4], bq[4];                                             // x_old (coalesced layout) and bias of the coming chunk
+    auto load_x = [&](int col) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + co_row + 8 * i;
+        xg[i] = (resid && r < shp.M) ? __ldcg(reinterpret_cast<const float4*>(epi.out_f32 + (long long)r * shp.N + col) + co_piece)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bq[q] = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + col) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (sub < n_chunks) load_x(n0 + sub * CW);           // x_old does not depend on the accumulator: in flight during the wait
+    if (resid && sub == 0) {
+      // x_old of this CTA's NEXT tile -> L2 (one BN * 4-byte row segment per lane): the register prefetch below then covers an
+      // L2 latency, not a DRAM one
+      const int pn = pr + (gridDim.x >> 1);
+      if (pn < n_pairs) {
+        const int rn = (2 * (pn / n_tiles_n) + cta_rank) * BM + quad * 32 + lane;
+        if (rn < shp.M)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                       ::"l"(epi.out_f32 + (long long)rn * shp.N + (pn % n_tiles_n) * BN), "r"(BN * 4) : "memory");
+      }
+    }
+    mbar_wait(&tmem_full[buf], use & 1u);
+    tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kMaxBN);
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = sub; j < n_chunks; j += kEpiPerQuad) {
+      const int c = j * CW;
+      const int col = n0 + c;
+      float v[CW];
+      tmem_ld16_nowait(t_row + (uint32_t)c, reinterpret_cast<uint32_t*>(v));
+      // x_old: coalesced registers -> fp32 tile -> row per lane
+      __syncwarp();                                        // the previous chunk's reads of the tile are done
+      if (resid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = co_row + 8 * i;
+          *reinterpret_cast<float4*>(xs + r * 64 + ((co_piece ^ ((r >> 1) & 3)) << 4)) = xg[i];
+        }
+      }
+      __syncwarp();
+      float4 xr[4], bc[4];
+      if (resid) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) xr[ch] = *reinterpret_cast<const float4*>(xs + rp_base + ((ch ^ rp_x) << 4));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bc[q] = bq[q];
+      if (j + kEpiPerQuad < n_chunks) load_x(n0 + (j + kEpiPerQuad) * CW);      // next chunk's x_old, one chunk ahead
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // the plain epilogue's operation order: acc * sc + bias, + table, then the residual add (x += v): same roundings
+        float* u = v + 4 * q;
+        if (epi.bias) {
+          const float4 b = bc[q];
+          u[0] = fmaf(u[0], sc, b.x); u[1] = fmaf(u[1], sc, b.y); u[2] = fmaf(u[2], sc, b.z); u[3] = fmaf(u[3], sc, b.w);
+        } else {
+          u[0] *= sc; u[1] *= sc; u[2] *= sc; u[3] *= sc;
+        }
+        if (table_row) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(table_row + col) + q);
+          u[0] += t.x; u[1] += t.y; u[2] += t.z; u[3] += t.w;
+        }
+        if (resid) { u[0] += xr[q].x; u[1] += xr[q].y; u[2] += xr[q].z; u[3] += xr[q].w; }
+      }
+#pragma unroll
+      for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+      // x_new: row per lane -> fp32 tile -> coalesced stores (each lane re-reads only what the warp wrote: __syncwarp suffices)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<float4*>(xs + rp_base + ((ch ^ rp_x) << 4)) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = co_row + 8 * i;
+        const float4 o = *reinterpret_cast<const float4*>(xs + r * 64 + ((co_piece ^ ((r >> 1) & 3)) << 4));
+        if (r0 + r < shp.M) reinterpret_cast<float4*>(epi.out_f32 + (long long)(r0 + r) * shp.N + col)[co_piece] = o;
+      }
+      // ---- operand planes of the same values -> plane tiles -> TMA store -------------------------------------
+      uint32_t hi[CW / 2], lo[CW / 2];
+      if (epi.out_fmt == kFmtF16F8) {
+#pragma unroll
+        for (int e = 0; e < CW / 2; ++e) split_f16f8_x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < CW / 2; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous chunk's planes have been read
+      __syncwarp();
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int off = lane * 32 + ((ch ^ ((lane >> 2) & 1)) << 4);                     // SWIZZLE_32B
+        *reinterpret_cast<uint4*>(ps + off) = make_uint4(hi[4 * ch], hi[4 * ch + 1], hi[4 * ch + 2], hi[4 * ch + 3]);
+        *reinterpret_cast<uint4*>(ps + 1024 + off) = make_uint4(lo[4 * ch], lo[4 * ch + 1], lo[4 * ch + 2], lo[4 * ch + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap_planes)), "r"(ps_addr), "r"(col), "r"(r0), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (row_ok && epi.stats_out && sub < n_chunks)
+      reinterpret_cast<float2*>(epi.stats_out)[(long long)row * kLnSlots + (n0 / BN) * kEpiPerQuad + sub] = make_float2(s1, s2);
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
 __global__ void __cluster_dims__(2, 1, 1) RIBCA_GEMM_BOUNDS
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_out, const GemmShape shp, const GemmEpilogue epi) {
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+                    const GemmShape shp, const GemmEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging_base = smem + kStages * kStageBytes;
@@ -298,6 +533,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_out);
+    if (epi.mode == RIBCA_EPI_STORE_LN || epi.mode == RIBCA_EPI_RESIDUAL_LN) prefetch_tmap(&tmap_out2);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * kEpiWarps); }   // both CTAs' epilogues
     fence_barrier_init();
@@ -382,8 +618,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
-    if (epi.chunk == 32) epilogue_loop<32>(tmap_out, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
-    else                 epilogue_loop<16>(tmap_out, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
+    if (epi.mode == RIBCA_EPI_STORE_LN || epi.mode == RIBCA_EPI_RESIDUAL_LN) {
+      epilogue_loop_ln(tmap_out2, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
+    } else if (epi.chunk == 32) epilogue_loop<32>(tmap_out, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
+    else                        epilogue_loop<16>(tmap_out, shp, epi, staging_base, tmem_base, tmem_full, tmem_empty, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -440,23 +678,51 @@ gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, long long a_plane, const _
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
     if (row >= shp.M) continue;
+    float mean = 0.f, rstd = 1.f;
+    if (epi.stats_in) ln_row_stats(epi.stats_in, row, epi.slots_in, epi.inv_dim, epi.ln_eps, mean, rstd);
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + tx * 4 + j;
       if (col >= shp.N) continue;
       float v = acc[i][j];
-      if (epi.bias) v += epi.bias[col];
+      if (epi.stats_in) v = fmaf(v, rstd, fmaf(-mean * rstd, epi.c1[col], epi.bias[col]));
+      else if (epi.bias) v += epi.bias[col];
       if (epi.row_table) v += epi.row_table[(long long)(row % epi.table_period) * shp.N + col];
       const long long o = (long long)row * shp.N + col;
       if (epi.mode == RIBCA_EPI_GELU) {
         split_bf16(gelu_erf(v), epi.out_hi[o], epi.out_lo[o]);
       } else if (epi.mode == RIBCA_EPI_STORE_SPLIT) {
         split_bf16(v, epi.out_hi[o], epi.out_lo[o]);
-      } else if (epi.mode == RIBCA_EPI_RESIDUAL) {
-        epi.out_f32[o] += v;
+      } else if (epi.mode == RIBCA_EPI_RESIDUAL || epi.mode == RIBCA_EPI_RESIDUAL_LN) {
+        epi.out_f32[o] += v;        // (*_LN on this path: planes and statistics follow in ln_planes_stats_kernel)
       } else {
         epi.out_f32[o] = v;
       }
     }
+  }
+}
+
+// SIMT companion of the *_LN epilogues (and their on-device cross-check): operand planes and the row statistics of fp32
+// rows, one warp per row; the whole row goes into slot 0
+__global__ void __launch_bounds__(256)
+ln_planes_stats_kernel(const float* __restrict__ x, int M, int D, int fmt, __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
+                       float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const float2* xr = reinterpret_cast<const float2*>(x + (long long)row * D);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < D / 2; i += 32) {
+      const float2 v = xr[i];
+      s1 += v.x + v.y;
+      s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2));
+      uint32_t a, b;
+      split_pair(v.x, v.y, fmt, a, b);
+      reinterpret_cast<uint32_t*>(p0 + (long long)row * D)[i] = a;
+      reinterpret_cast<uint32_t*>(p1 + (long long)row * D)[i] = b;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) reinterpret_cast<float2*>(stats)[(long long)row * kLnSlots] = make_float2(s1, s2);
   }
 }
 
@@ -518,13 +784,23 @@ int pick_bn(int N) {
   return 0;
 }
 
+// slots a *_LN epilogue of width N fills (tcgen05 path: two per N tile; SIMT path: one)
+int gemm_ln_slots(int N, int precision) { return precision == RIBCA_SIMT_FP32 ? 1 : 2 * (N / pick_bn(N)); }
+
 int gemm_launch(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
                 const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
-                void* out_split, long long out_plane, int precision, int w_log2_scale, cudaStream_t stream) {
+                void* out_split, long long out_plane, int precision, int w_log2_scale, cudaStream_t stream,
+                const ribca_ln_fold* ln) {
   RIBCA_REQUIRE(A && W, "gemm: null operand");
+  const bool ln_out = epilogue == RIBCA_EPI_STORE_LN || epilogue == RIBCA_EPI_RESIDUAL_LN;
+  const bool ln_in = ln && ln->stats_in;
+  RIBCA_REQUIRE(!ln_out || (ln && ln->stats_out && out_f32 && out_split), "gemm: a *_LN epilogue needs out_f32, out_split and ln->stats_out");
+  RIBCA_REQUIRE(!ln_in || (ln->c1 && bias && ln->slots_in > 0 && ln->slots_in <= RIBCA_LN_SLOTS && !row_table && !ln_out),
+                "gemm: a LayerNorm-folded GEMM needs c1, c2 (as bias) and 1..%d statistics slots", RIBCA_LN_SLOTS);
   RIBCA_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RIBCA_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm: N=%d must be a multiple of 16 and K=%d of 8", N, K);
   const bool split_out = epilogue == RIBCA_EPI_GELU || epilogue == RIBCA_EPI_STORE_SPLIT;
+  RIBCA_REQUIRE(epilogue >= RIBCA_EPI_STORE && epilogue <= RIBCA_EPI_RESIDUAL_LN, "gemm: unknown epilogue %d", epilogue);
   RIBCA_REQUIRE(split_out ? (out_split != nullptr) : (out_f32 != nullptr), "gemm: output is null");
   RIBCA_REQUIRE(!row_table || table_period > 0, "gemm: row table needs a period");
   RIBCA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
@@ -543,7 +819,13 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
   epi.out_hi = static_cast<__nv_bfloat16*>(out_split);
   epi.out_lo = out_split ? static_cast<__nv_bfloat16*>(out_split) + out_plane : nullptr;
   // f16f8: a GELU output feeds the next GEMM (same format); a plain split store feeds attention (bf16 {hi, lo})
-  epi.out_fmt = (precision == RIBCA_F16F8 && epilogue == RIBCA_EPI_GELU) ? kFmtF16F8 : kFmtBf16;
+  epi.out_fmt = (precision == RIBCA_F16F8 && (epilogue == RIBCA_EPI_GELU || ln_out)) ? kFmtF16F8 : kFmtBf16;
+  epi.stats_in = ln_in ? ln->stats_in : nullptr;
+  epi.c1 = ln_in ? ln->c1 : nullptr;
+  epi.slots_in = ln_in ? ln->slots_in : 0;
+  epi.inv_dim = 1.0f / (float)K;
+  epi.ln_eps = ln ? ln->eps : 0.f;
+  epi.stats_out = ln_out ? ln->stats_out : nullptr;
   RIBCA_REQUIRE(w_log2_scale > -64 && w_log2_scale < 64, "gemm: weight scale exponent %d out of range", w_log2_scale);
   epi.acc_scale = precision == RIBCA_F16F8 ? ldexpf(1.0f, -w_log2_scale) : 1.0f;
 
@@ -552,21 +834,30 @@ int gemm_launch(const void* A, long long a_plane, const void* W, long long w_pla
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), a_plane,
                                                static_cast<const __nv_bfloat16*>(W), w_plane, shp, epi);
     RIBCA_LAUNCH_CHECK("gemm_simt_kernel");
+    if (ln_out) {
+      ln_planes_stats_kernel<<<std::min((M + 7) / 8, num_sms() * 8), 256, 0, stream>>>(out_f32, M, N, kFmtBf16, epi.out_hi, epi.out_lo, ln->stats_out);
+      RIBCA_LAUNCH_CHECK("ln_planes_stats_kernel");
+    }
     return RIBCA_OK;
   }
   RIBCA_REQUIRE(precision == RIBCA_BF16X3 || precision == RIBCA_BF16X1 || precision == RIBCA_F16F8, "gemm: unknown precision %d", precision);
-  CUtensorMap map_a, map_w, map_out;
+  CUtensorMap map_a, map_w, map_out, map_out2;
+  memset(&map_out2, 0, sizeof(map_out2));
   RIBCA_TRY(make_operand_map(&map_a, A, a_plane, M, K, BM, shp.n_planes));
   RIBCA_TRY(make_operand_map(&map_w, W, w_plane, N, K, shp.BN / 2, shp.n_planes));      // each CTA of a pair stages half of the W tile
   epi.chunk = (shp.BN % 32 == 0 && !RIBCA_FORCE_CW16) ? 32 : 16;
   RIBCA_REQUIRE(!split_out || (out_plane * 2) % 16 == 0, "gemm: split output plane stride must be 16-byte aligned");
   RIBCA_TRY(make_output_map(&map_out, split_out, split_out ? out_split : (void*)out_f32, out_plane, M, N, epi.chunk));
+  if (ln_out) {
+    RIBCA_REQUIRE((out_plane * 2) % 16 == 0, "gemm: plane stride of the *_LN planes must be 16-byte aligned");
+    RIBCA_TRY(make_output_map(&map_out2, true, out_split, out_plane, M, N, 16));      // the *_LN epilogue works in 16-column chunks
+  }
   RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel), (int)(kSmemBytes), "cudaFuncSetAttribute(gemm_tcgen05_kernel)"));
   const int n_pairs = (((M + BM - 1) / BM + 1) / 2) * (N / shp.BN);
   const int grid = 2 * std::min(n_pairs, num_sms() / 2);
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_GEMM, 2.0 * (double)M * (double)N * (double)K, stream);
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, map_out, shp, epi);
+  gemm_tcgen05_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(map_a, map_w, map_out, map_out2, shp, epi);
   if (prof) prof_end_span(stream);
   RIBCA_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return RIBCA_OK;
@@ -618,7 +909,20 @@ int ribca_gemm_splitbf16(const void* A, long long a_plane, const void* W, long l
                          float* out_f32, void* out_split, long long out_plane, int precision, int w_log2_scale,
                          ribca_stream_t stream) {
   return gemm_launch(A, a_plane, W, w_plane, M, N, K, bias, row_table, table_period, epilogue, out_f32, out_split,
-                     out_plane, precision, w_log2_scale, as_stream(stream));
+                     out_plane, precision, w_log2_scale, as_stream(stream), nullptr);
+}
+
+int ribca_gemm_ln(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
+                  const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
+                  void* out_split, long long out_plane, int precision, int w_log2_scale, const ribca_ln_fold* ln,
+                  ribca_stream_t stream) {
+  return gemm_launch(A, a_plane, W, w_plane, M, N, K, bias, row_table, table_period, epilogue, out_f32, out_split,
+                     out_plane, precision, w_log2_scale, as_stream(stream), ln);
+}
+
+int ribca_gemm_ln_slots(int N, int precision) {
+  RIBCA_REQUIRE(N > 0 && N % 16 == 0 && ribca::pick_bn(N) > 0, "ribca_gemm_ln_slots: bad N=%d", N);
+  return gemm_ln_slots(N, precision);
 }
 
 int ribca_split_planes(const float* x, long long n, int format, int w_role, int log2_scale, void* plane0, void* plane1,

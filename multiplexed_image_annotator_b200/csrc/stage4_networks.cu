@@ -13,7 +13,9 @@ namespace ribca {
 
 int gemm_launch(const void* A, long long a_plane, const void* W, long long w_plane, int M, int N, int K,
                 const float* bias, const float* row_table, int table_period, int epilogue, float* out_f32,
-                void* out_split, long long out_plane, int precision, int w_log2_scale, cudaStream_t stream);
+                void* out_split, long long out_plane, int precision, int w_log2_scale, cudaStream_t stream,
+                const ribca_ln_fold* ln = nullptr);
+int gemm_ln_slots(int N, int precision);
 
 int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, int tokens, int heads, int hd,
                         void* out_split, long long out_plane, int out_fmt, cudaStream_t st);
@@ -478,17 +480,25 @@ constexpr int kInterleaveMinCells = 512;   // below this the GEMMs are too short
 
 struct BlockBuffers {
   float* x;          // [M][D]
-  bf16* a;           // split [2][M][D]
+  bf16* a;           // split [2][M][D]: LayerNorm output, then the attention output
   float* qkv;        // [M][3D]
   bf16* h;           // split [2][M][4D]
+  bf16* xa;          // LayerNorm-folded flow: operand planes [2][M][D] of the RAW residual stream x ...
+  float* stats;      // ... and its per-row partial sums [M][RIBCA_LN_SLOTS][2] (both written by the *_LN epilogues)
 };
 
 // timm Block x depth: x += proj(attn(LN1 x)); x += fc2(gelu(fc1(LN2 x)))
 // cls_rows != nullptr: the last block computes proj / MLP for the class-token rows only and leaves them,
 // compacted, in *cls_rows ([cells][D] fp32, carved from the MLP buffer)
+// folded: no LayerNorm kernel.  The GEMM that writes x (patch embedding before the first block, proj, fc2: *_LN epilogues)
+// also leaves the operand planes of the raw x in b.xa and its row statistics in b.stats; qkv and fc1 contract those planes
+// with W * diag(gamma) and apply mean / rstd / beta in their epilogue (include/ribca_b200.h: ribca_ln_fold).
 static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int heads, int cells, int tokens,
                       const float* wf32, const bf16* wsplit, long long split_plane, const BlockBuffers& b,
-                      int precision, int wls, cudaStream_t st, float** cls_rows = nullptr) {
+                      int precision, int wls, cudaStream_t st, float** cls_rows = nullptr, int fold_mask = 0) {
+  const bool fold1 = (fold_mask & 1) != 0;      // norm1 inside the qkv GEMM (producers: patch embedding, fc2)
+  const bool fold2 = (fold_mask & 2) != 0;      // norm2 inside the fc1 GEMM (producer: proj)
+  const bool folded = fold_mask != 0;
   const int M = cells * tokens;
   const int fmt = fmt_of(precision);
   const long long pa = (long long)M * D, ph = (long long)M * 4 * D;
@@ -496,14 +506,24 @@ static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int head
   const int Wq = 3 * heads * hdp;                       // head-padded qkv width
   const bool tensor_attention = tokens > 32 && tokens <= 112;   // tcgen05 for the classifiers, FP32 pipe for the imputer
   RIBCA_REQUIRE(tensor_attention || hdp == hd, "short-sequence attention needs head_dim %% 16 == 0");
+  RIBCA_REQUIRE(!folded || tensor_attention, "the LayerNorm-folded flow is the classifiers' (tensor-core attention)");
+  const int slots = folded ? gemm_ln_slots(D, precision) : 0;      // every producer of x has N = D
+  ribca_ln_fold ln_in{b.stats, nullptr, slots, 1e-6f, nullptr};  // consumer side (c1 set per GEMM)
+  const ribca_ln_fold ln_out{nullptr, nullptr, 0, 1e-6f, b.stats};
   for (int l = 0; l < depth; ++l) {
     const ribca_block_desc& w = blocks[l];
-    RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln1_g, wf32 + w.ln1_b, 1e-6f, b.a, pa, fmt, st));
+    if (!fold1) RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln1_g, wf32 + w.ln1_b, 1e-6f, b.a, pa, fmt, st));
     if (tensor_attention) {
       bf16* qs = reinterpret_cast<bf16*>(b.qkv);
       const long long pq = (long long)M * Wq;
-      RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
-                            RIBCA_EPI_STORE_SPLIT, nullptr, qs, pq, precision, wls, st));
+      if (fold1) {
+        ln_in.c1 = wf32 + w.qkv_c1;
+        RIBCA_TRY(gemm_launch(b.xa, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_c2, nullptr, 0,
+                              RIBCA_EPI_STORE_SPLIT, nullptr, qs, pq, precision, wls, st, &ln_in));
+      } else {
+        RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
+                              RIBCA_EPI_STORE_SPLIT, nullptr, qs, pq, precision, wls, st));
+      }
       RIBCA_TRY(attention_tc_launch(qs, pq, cells, tokens, heads, hd, b.a, pa, fmt, st));
     } else {
       RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.qkv_w, split_plane, M, Wq, D, wf32 + w.qkv_b, nullptr, 0,
@@ -512,23 +532,53 @@ static int run_blocks(const ribca_block_desc* blocks, int depth, int D, int head
     }
     if (cls_rows && l == depth - 1) {
       // compact buffers inside the (idle) MLP buffer: x_cls fp32 [cells][D], a_cls planes [2][cells][D], h_cls planes [2][cells][4D]
+      // (+ folded: xa_cls planes [2][cells][D]; the statistics of the compact rows reuse the head of b.stats)
       char* base = reinterpret_cast<char*>(b.h);
       float* x_cls = reinterpret_cast<float*>(base);
       bf16* a_cls = reinterpret_cast<bf16*>(base + align_up((size_t)cells * D * 4, 256));
       bf16* h_cls = reinterpret_cast<bf16*>(reinterpret_cast<char*>(a_cls) + align_up((size_t)cells * D * 4, 256));
+      bf16* xa_cls = reinterpret_cast<bf16*>(reinterpret_cast<char*>(h_cls) + align_up((size_t)cells * D * 16, 256));
       const long long pc = (long long)cells * D, phc = (long long)cells * 4 * D;
       gather_cls_rows_kernel<<<grid_for((long long)cells * (D / 4), 256), 256, 0, st>>>(
           b.x, reinterpret_cast<const uint16_t*>(b.a), pa, cells, tokens, D, x_cls, reinterpret_cast<uint16_t*>(a_cls), pc);
       RIBCA_LAUNCH_CHECK("gather_cls_rows_kernel");
-      RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.proj_w, split_plane, cells, D, D, wf32 + w.proj_b, nullptr, 0,
-                            RIBCA_EPI_RESIDUAL, x_cls, nullptr, 0, precision, wls, st));
-      RIBCA_TRY(layernorm_launch(x_cls, cells, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, a_cls, pc, fmt, st));
-      RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.fc1_w, split_plane, cells, 4 * D, D, wf32 + w.fc1_b, nullptr, 0,
-                            RIBCA_EPI_GELU, nullptr, h_cls, phc, precision, wls, st));
+      if (fold2) {
+        RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.proj_w, split_plane, cells, D, D, wf32 + w.proj_b, nullptr, 0,
+                              RIBCA_EPI_RESIDUAL_LN, x_cls, xa_cls, pc, precision, wls, st, &ln_out));
+        ln_in.c1 = wf32 + w.fc1_c1;
+        RIBCA_TRY(gemm_launch(xa_cls, pc, wsplit + w.fc1_w, split_plane, cells, 4 * D, D, wf32 + w.fc1_c2, nullptr, 0,
+                              RIBCA_EPI_GELU, nullptr, h_cls, phc, precision, wls, st, &ln_in));
+      } else {
+        RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.proj_w, split_plane, cells, D, D, wf32 + w.proj_b, nullptr, 0,
+                              RIBCA_EPI_RESIDUAL, x_cls, nullptr, 0, precision, wls, st));
+        RIBCA_TRY(layernorm_launch(x_cls, cells, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, a_cls, pc, fmt, st));
+        RIBCA_TRY(gemm_launch(a_cls, pc, wsplit + w.fc1_w, split_plane, cells, 4 * D, D, wf32 + w.fc1_b, nullptr, 0,
+                              RIBCA_EPI_GELU, nullptr, h_cls, phc, precision, wls, st));
+      }
       RIBCA_TRY(gemm_launch(h_cls, phc, wsplit + w.fc2_w, split_plane, cells, D, 4 * D, wf32 + w.fc2_b, nullptr, 0,
                             RIBCA_EPI_RESIDUAL, x_cls, nullptr, 0, precision, wls, st));
       *cls_rows = x_cls;
       return RIBCA_OK;
+    }
+    if (folded) {
+      if (fold2) {
+        RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
+                              RIBCA_EPI_RESIDUAL_LN, b.x, b.xa, pa, precision, wls, st, &ln_out));
+        ln_in.c1 = wf32 + w.fc1_c1;
+        RIBCA_TRY(gemm_launch(b.xa, pa, wsplit + w.fc1_w, split_plane, M, 4 * D, D, wf32 + w.fc1_c2, nullptr, 0,
+                              RIBCA_EPI_GELU, nullptr, b.h, ph, precision, wls, st, &ln_in));
+      } else {
+        RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
+                              RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, wls, st));
+        RIBCA_TRY(layernorm_launch(b.x, M, D, wf32 + w.ln2_g, wf32 + w.ln2_b, 1e-6f, b.a, pa, fmt, st));
+        RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.fc1_w, split_plane, M, 4 * D, D, wf32 + w.fc1_b, nullptr, 0,
+                              RIBCA_EPI_GELU, nullptr, b.h, ph, precision, wls, st));
+      }
+      // fc2 leaves the next block's norm1 inputs (planes + statistics) when norm1 is folded
+      RIBCA_TRY(gemm_launch(b.h, ph, wsplit + w.fc2_w, split_plane, M, D, 4 * D, wf32 + w.fc2_b, nullptr, 0,
+                            fold1 ? RIBCA_EPI_RESIDUAL_LN : RIBCA_EPI_RESIDUAL, b.x, fold1 ? b.xa : nullptr, fold1 ? pa : 0, precision, wls, st,
+                            fold1 ? &ln_out : nullptr));
+      continue;
     }
     RIBCA_TRY(gemm_launch(b.a, pa, wsplit + w.proj_w, split_plane, M, D, D, wf32 + w.proj_b, nullptr, 0,
                           RIBCA_EPI_RESIDUAL, b.x, nullptr, 0, precision, wls, st));
@@ -551,12 +601,14 @@ struct Carver {
   }
 };
 
-static size_t block_buffers(Carver& cv, BlockBuffers& b, long long M, int D, int heads) {
+static size_t block_buffers(Carver& cv, BlockBuffers& b, long long M, int D, int heads, bool folded = false) {
   const int hdp = (D / heads + 15) / 16 * 16;
   b.x = cv.take<float>(M * D);
   b.a = cv.take<bf16>(2 * M * D);
   b.qkv = cv.take<float>(M * 3 * heads * hdp);     // fp32 [M][3D] or split-bf16 [2][M][3*heads*hdp]: same bytes
   b.h = cv.take<bf16>(2 * M * 4 * D);
+  b.xa = folded ? cv.take<bf16>(2 * M * D) : nullptr;
+  b.stats = folded ? cv.take<float>(M * RIBCA_LN_SLOTS * 2) : nullptr;
   return cv.off;
 }
 
@@ -587,13 +639,14 @@ size_t ribca_vit_workspace_bytes(const ribca_vit_desc* desc, int n_cells) {
   if (!desc || n_cells <= 0) return 0;
   Carver cv{nullptr, 0};
   BlockBuffers b;
-  block_buffers(cv, b, (long long)n_cells * desc->tokens, desc->dim, desc->heads);
+  const bool folded = desc->ln_folded != 0;
+  block_buffers(cv, b, (long long)n_cells * desc->tokens, desc->dim, desc->heads, folded);
   size_t need = cv.off;
   const int n0 = interleave_split(n_cells);
   if (n0 > 0) {
     Carver c2{nullptr, 0};
-    block_buffers(c2, b, (long long)n0 * desc->tokens, desc->dim, desc->heads);
-    block_buffers(c2, b, (long long)(n_cells - n0) * desc->tokens, desc->dim, desc->heads);
+    block_buffers(c2, b, (long long)n0 * desc->tokens, desc->dim, desc->heads, folded);
+    block_buffers(c2, b, (long long)(n_cells - n0) * desc->tokens, desc->dim, desc->heads, folded);
     need = std::max(need, c2.off);
   }
   return align_up(need, 256);
@@ -610,10 +663,17 @@ static int vit_forward_range(const ribca_vit_desc* desc, const float* wf32, cons
   const int fmt = fmt_of(precision), wls = desc->w_log2_scale;
   im2col_split_kernel<<<grid_for((long long)n_cells * C * 400, 256), 256, 0, st>>>(patches, n_cells, C, fmt, b.h, b.h + pe_plane);
   RIBCA_LAUNCH_CHECK("im2col_split_kernel");
-  RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
-                        wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, wls, st));
+  const int folded = desc->ln_folded;
+  if (folded & 1) {
+    const ribca_ln_fold ln_out{nullptr, nullptr, 0, 1e-6f, b.stats};
+    RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
+                          wf32 + desc->embed_table, T, RIBCA_EPI_STORE_LN, b.x, b.xa, M * D, precision, wls, st, &ln_out));
+  } else {
+    RIBCA_TRY(gemm_launch(b.h, pe_plane, wsplit + desc->embed_w, desc->split_plane, (int)M, D, Kpe, nullptr,
+                          wf32 + desc->embed_table, T, RIBCA_EPI_STORE, b.x, nullptr, 0, precision, wls, st));
+  }
   float* x_cls = nullptr;
-  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st, &x_cls));
+  RIBCA_TRY(run_blocks(desc->blocks, desc->depth, D, desc->heads, n_cells, T, wf32, wsplit, desc->split_plane, b, precision, wls, st, &x_cls, folded));
   head_softmax_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x_cls, n_cells, 1, D, wf32 + desc->norm_g, wf32 + desc->norm_b, 1e-6f,
                                                          wf32 + desc->head_w, wf32 + desc->head_b, desc->classes, probs, logits);
   RIBCA_LAUNCH_CHECK("head_softmax_kernel");
@@ -649,19 +709,21 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
     return vit_forward_f32(desc, wf32, static_cast<const float*>(wsplit_), patches, n_cells, probs, logits, b.x,
                            reinterpret_cast<float*>(b.a), b.qkv, reinterpret_cast<float*>(b.h), st);
   }
+  RIBCA_REQUIRE(!desc->ln_folded || desc->dim % 32 == 0 || desc->dim % 16 == 0, "ribca_vit_forward: dim %d", desc->dim);
   RIBCA_REQUIRE(desc->plane_format == fmt_of(precision), "ribca_vit_forward: weights are packed in plane format %d but precision %d needs %d",
                 desc->plane_format, precision, fmt_of(precision));
   const int n0 = interleave_enabled() ? interleave_split(n_cells) : 0;
+  const bool folded = desc->ln_folded != 0;
   if (n0 == 0) {
     BlockBuffers b;
-    block_buffers(cv, b, M, D, desc->heads);
+    block_buffers(cv, b, M, D, desc->heads, folded);
     return vit_forward_range(desc, wf32, wsplit, patches, n_cells, probs, logits, b, precision, st);
   }
   // two-way interleave: half 0 on the caller's stream, half 1 on the side stream (include/ribca_b200.h: ribca_set_interleave)
   const int n1 = n_cells - n0;
   BlockBuffers b0, b1;
-  block_buffers(cv, b0, (long long)n0 * T, D, desc->heads);
-  block_buffers(cv, b1, (long long)n1 * T, D, desc->heads);
+  block_buffers(cv, b0, (long long)n0 * T, D, desc->heads, folded);
+  block_buffers(cv, b1, (long long)n1 * T, D, desc->heads, folded);
   SideStream side;
   RIBCA_TRY(side_stream(&side));
   RIBCA_TRY(check_cuda(cudaEventRecord(side.fork, st), "cudaEventRecord(fork)"));

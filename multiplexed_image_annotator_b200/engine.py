@@ -8,6 +8,7 @@ C descriptor of element offsets (include/ribca_b200.h: ribca_vit_desc / ribca_ma
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -19,6 +20,7 @@ class _Packer:
     def __init__(self):
         self.f32, self.f32_off = [], 0
         self.mat, self.mat_off = [], 0
+        self.folds = []          # (matrix offset, rows, cols, gamma): matrices that take W * diag(gamma) in the tensor-core packings
 
     @staticmethod
     def _pad(t, mult=64):
@@ -46,12 +48,17 @@ class _Packer:
         return torch.cat(self.f32).to(device), torch.cat(self.mat)
 
 
-def pack_matrices(mats_host: torch.Tensor, fmt: int, device):
+def pack_matrices(mats_host: torch.Tensor, fmt: int, device, folds=()):
     """GEMM matrices -> (device operand blob, w_log2_scale) in `fmt`: two 16-bit planes (2, total) for the tensor-core
-    formats, the plain fp32 blob for RIBCA_PLANES_F32 (the FP32-pipe re-evaluation path)."""
-    mats = mats_host.to(device)
+    formats, the plain fp32 blob for RIBCA_PLANES_F32 (the FP32-pipe re-evaluation path).  `folds`: matrices that are packed
+    as W * diag(gamma) in the tensor-core formats (LayerNorm folded into its consumer GEMM, ribca_ln_fold)."""
     if fmt == ops.FMT_F32:
-        return mats, 0
+        return mats_host.to(device), 0
+    if folds:
+        mats_host = mats_host.clone()
+        for off, rows, cols, gamma in folds:
+            mats_host[off:off + rows * cols].view(rows, cols).mul_(gamma[None, :])
+    mats = mats_host.to(device)
     if fmt == ops.FMT_BF16:
         return ops.split_bf16(mats), 0
     t = ops.weight_log2_scale(float(mats.abs().max().item()))
@@ -62,8 +69,9 @@ class _Packs:
     """The packed weights of one network per operand format, built lazily: the default precision at construction, the
     higher-precision formats the first time a re-evaluation asks for them (pipeline.refine_labels)."""
 
-    def __init__(self, desc, mats_host, plane_elems, device):
-        self._desc, self._mats, self._plane, self._device = desc, mats_host, plane_elems, device
+    def __init__(self, desc, mats_host, plane_elems, device, folds=(), fold_mask: int = 0):
+        self._desc, self._mats, self._plane, self._device, self._folds = desc, mats_host, plane_elems, device, tuple(folds)
+        self._fold_mask = fold_mask
         self._by_fmt = {}
 
     def get(self, precision: str):
@@ -72,8 +80,10 @@ class _Packs:
         if fmt not in self._by_fmt:
             d = type(self._desc)()
             C.memmove(C.byref(d), C.byref(self._desc), C.sizeof(d))
-            blob, d.w_log2_scale = pack_matrices(self._mats, fmt, self._device)
+            blob, d.w_log2_scale = pack_matrices(self._mats, fmt, self._device, self._folds)
             d.plane_format, d.split_plane = fmt, self._plane
+            if hasattr(d, "ln_folded"):
+                d.ln_folded = self._fold_mask if (self._folds and fmt != ops.FMT_F32) else 0
             self._by_fmt[fmt] = (d, blob)
         return self._by_fmt[fmt]
 
@@ -91,13 +101,32 @@ def _pad_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
     return out.reshape(3 * heads * hdp, *t.shape[1:])
 
 
-def _pack_block(pk: _Packer, sd, prefix: str, desc: _lib.BlockDesc, heads: int):
+def _fold_vectors(w, b, gamma, beta):
+    """LayerNorm(x; gamma, beta) @ w.T + b = rstd * (x @ (w * gamma).T - mean * c1) + c2 -> (c1, c2), fp64 sums."""
+    wg = (w * gamma[None, :]).to(torch.float32)                 # the matrix that is packed (pack_matrices applies the same product)
+    c1 = wg.double().sum(1).to(torch.float32)
+    c2 = (b.double() + w.double() @ beta.double()).to(torch.float32)
+    return c1, c2
+
+
+def _pack_block(pk: _Packer, sd, prefix: str, desc: _lib.BlockDesc, heads: int, fold: int = 0):
     desc.ln1_g = pk.add_f32(sd[f"{prefix}.norm1.weight"]); desc.ln1_b = pk.add_f32(sd[f"{prefix}.norm1.bias"])
     desc.ln2_g = pk.add_f32(sd[f"{prefix}.norm2.weight"]); desc.ln2_b = pk.add_f32(sd[f"{prefix}.norm2.bias"])
     desc.qkv_b = pk.add_f32(_pad_heads(sd[f"{prefix}.attn.qkv.bias"], heads)); desc.proj_b = pk.add_f32(sd[f"{prefix}.attn.proj.bias"])
     desc.fc1_b = pk.add_f32(sd[f"{prefix}.mlp.fc1.bias"]); desc.fc2_b = pk.add_f32(sd[f"{prefix}.mlp.fc2.bias"])
     desc.qkv_w = pk.add_mat(_pad_heads(sd[f"{prefix}.attn.qkv.weight"], heads)); desc.proj_w = pk.add_mat(sd[f"{prefix}.attn.proj.weight"])
     desc.fc1_w = pk.add_mat(sd[f"{prefix}.mlp.fc1.weight"]); desc.fc2_w = pk.add_mat(sd[f"{prefix}.mlp.fc2.weight"])
+    g1, b1, g2, b2 = (sd[f"{prefix}.norm{i}.{n}"] for i in (1, 2) for n in ("weight", "bias"))
+    dim = g1.numel()
+    if fold & 1:
+        c1, c2 = _fold_vectors(sd[f"{prefix}.attn.qkv.weight"], sd[f"{prefix}.attn.qkv.bias"], g1, b1)
+        desc.qkv_c1 = pk.add_f32(_pad_heads(c1, heads)); desc.qkv_c2 = pk.add_f32(_pad_heads(c2, heads))
+        qkv_rows = _pad_heads(sd[f"{prefix}.attn.qkv.weight"], heads).shape[0]
+        pk.folds.append((desc.qkv_w, qkv_rows, dim, g1.to(torch.float32)))
+    if fold & 2:
+        c1, c2 = _fold_vectors(sd[f"{prefix}.mlp.fc1.weight"], sd[f"{prefix}.mlp.fc1.bias"], g2, b2)
+        desc.fc1_c1 = pk.add_f32(c1); desc.fc1_c2 = pk.add_f32(c2)
+        pk.folds.append((desc.fc1_w, sd[f"{prefix}.mlp.fc1.weight"].shape[0], dim, g2.to(torch.float32)))
 
 
 class _Workspace:
@@ -142,10 +171,16 @@ class VitEngine:
         d.embed_w = pk.add_mat(sd["patch_embed.proj.weight"].reshape(s.dim, -1))
         d.norm_g = pk.add_f32(sd["norm.weight"]); d.norm_b = pk.add_f32(sd["norm.bias"])
         d.head_w = pk.add_f32(sd["head.weight"]); d.head_b = pk.add_f32(sd["head.bias"])
+        # LayerNorm folded into its consumer GEMM (ribca_ln_fold): bit 0 = norm1 into qkv (fc2 / the patch embedding leave the
+        # planes + row statistics), bit 1 = norm2 into fc1 (proj leaves them).  Opt-in: measured neutral (mask 1) to -1 % (mask 3)
+        # on the power-capped B200s of this pool - the epilogue work it adds to the GEMMs costs what the LayerNorm kernels
+        # it removes cost (profiles/r02_lnfold.md)
+        fold = int(os.environ.get("RIBCA_LN_FOLD", "0")) & 3
         for i in range(s.depth):
-            _pack_block(pk, sd, f"blocks.{i}", d.blocks[i], s.heads)
+            _pack_block(pk, sd, f"blocks.{i}", d.blocks[i], s.heads, fold=fold)
         self.wf32, mats = pk.finish(self.device)
-        self._packs = _Packs(d, mats, pk.mat_off, self.device)
+        self.ln_fold = fold
+        self._packs = _Packs(d, mats, pk.mat_off, self.device, pk.folds, fold)
         self.desc, self.wsplit = self._packs.get(precision)
 
     def set_head(self, weight: torch.Tensor, bias: torch.Tensor):

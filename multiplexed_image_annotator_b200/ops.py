@@ -34,7 +34,7 @@ def weight_log2_scale(max_abs: float) -> int:
     if not max_abs > 0.0 or not math.isfinite(max_abs):
         return 0
     return int(max(-20, min(30, math.floor(math.log2(128.0 / max_abs)))))
-EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_STORE_SPLIT = 0, 1, 2, 3
+EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_STORE_SPLIT, EPI_STORE_LN, EPI_RESIDUAL_LN = 0, 1, 2, 3, 4, 5
 _DTYPES = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2, torch.int32: 3}
 
 
@@ -399,6 +399,41 @@ def gemm(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None
     _lib.check(_lib.lib().ribca_gemm_splitbf16(_ptr(a_split), m * k, _ptr(w_split), n * k, m, n, k, _ptr(bias), _ptr(row_table),
                                                period, epilogue, _ptr(out_f32), _ptr(out_split), m * n, PRECISION[precision],
                                                int(w_log2_scale), _stream()), "ribca_gemm_splitbf16")
+    return out_split if epilogue in (EPI_GELU, EPI_STORE_SPLIT) else out_f32
+
+
+def gemm_ln(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, row_table=None, epilogue=EPI_STORE, out=None,
+            precision="bf16x3", w_log2_scale: int = 0, stats_in=None, c1=None, slots_in: int = 0, eps: float = 1e-6):
+    """ribca_gemm_ln: the GEMMs around a folded LayerNorm.
+    Producer (epilogue EPI_STORE_LN / EPI_RESIDUAL_LN): returns (x fp32 (M, N) [`out` += for the residual form], planes of x
+    (2, M, N) in the format of `precision`, stats (M, LN_SLOTS, 2), filled slots).
+    Consumer (stats_in, c1, slots_in given; bias = c2): like gemm() with v = rstd * (acc - mean * c1) + c2."""
+    _need_cuda(a_split, w_split, bias, row_table, out, stats_in, c1)
+    _, m, k = a_split.shape
+    _, n, k2 = w_split.shape
+    assert k == k2
+    dev = a_split.device
+    L = _lib.lib()
+    ln = _lib.LnFold()
+    ln.stats_in, ln.c1, ln.slots_in, ln.eps = _ptr(stats_in) or None, _ptr(c1) or None, int(slots_in), float(eps)
+    ln_out = epilogue in (EPI_STORE_LN, EPI_RESIDUAL_LN)
+    out_f32 = out_split = stats = None
+    fmt = plane_format(precision)
+    if ln_out:
+        out_f32 = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=dev)
+        out_split = _planes((m, n), fmt, dev)
+        stats = torch.zeros((m, _lib.LN_SLOTS, 2), dtype=torch.float32, device=dev)
+        ln.stats_out = _ptr(stats)
+    elif epilogue in (EPI_GELU, EPI_STORE_SPLIT):
+        out_split = _planes((m, n), fmt if epilogue == EPI_GELU else FMT_BF16, dev)
+    else:
+        out_f32 = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=dev)
+    period = row_table.shape[0] if row_table is not None else 0
+    _lib.check(L.ribca_gemm_ln(_ptr(a_split), m * k, _ptr(w_split), n * k, m, n, k, _ptr(bias), _ptr(row_table), period, epilogue,
+                               _ptr(out_f32), _ptr(out_split), m * n, PRECISION[precision], int(w_log2_scale), C.byref(ln), _stream()),
+               "ribca_gemm_ln")
+    if ln_out:
+        return out_f32, out_split, stats, int(L.ribca_gemm_ln_slots(n, PRECISION[precision]))
     return out_split if epilogue in (EPI_GELU, EPI_STORE_SPLIT) else out_f32
 
 

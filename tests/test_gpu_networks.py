@@ -128,6 +128,102 @@ def test_gemm_tcgen05_f16f8_epilogues(epilogue, period):
     assert rel < 2.0 ** -13        # + the output's own quantisation (2^-15 relative for the f16f8 planes)
 
 
+def _planes_value(t, precision):
+    return _unsplit_f16f8(t) if precision == "f16f8" else _unsplit(t)
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3", "simt"])
+@pytest.mark.parametrize("m,d,k,resid,period", [(101 * 9, 576, 576, True, 0), (333, 288, 1152, True, 0), (101 * 3, 576, 240, False, 101),
+                                                (1000, 144, 144, True, 0), (260, 384, 384, True, 0)])
+def test_gemm_ln_producer_epilogues(precision, m, d, k, resid, period):
+    """RIBCA_EPI_RESIDUAL_LN / STORE_LN (proj, fc2, patch embedding of the LayerNorm-folded flow): the fp32 rows are
+    x_old + (A W^T + b) with the same two roundings as the reduce-add epilogue, the planes are the split of exactly the stored
+    values, and the slot sums add up to the row's sum / sum of squares."""
+    g = torch.Generator(device=DEV).manual_seed(m + d)
+    a = torch.randn((m, k), generator=g, device=DEV)
+    w = torch.randn((d, k), generator=g, device=DEV) * 0.05
+    b = None if period else torch.randn(d, generator=g, device=DEV)
+    tab = torch.randn((period, d), generator=g, device=DEV) if period else None
+    x0 = torch.randn((m, d), generator=g, device=DEV) * 3 + 0.5
+    fmt = ops.plane_format(precision)
+    kw = dict(precision=precision)
+    if precision == "f16f8":
+        t = ops.weight_log2_scale(float(w.abs().max().item()))
+        a_s, w_s = ops.split_planes(a, fmt), ops.split_planes(w, fmt, w_role=True, log2_scale=t)
+        kw["w_log2_scale"] = t + 8
+    else:
+        a_s, w_s = ops.split_bf16(a), ops.split_bf16(w)
+    # the plain epilogue of the same GEMM is the reference for the fp32 rows: bit-identical
+    plain = ops.gemm(a_s, w_s, b, tab, ops.EPI_RESIDUAL if resid else ops.EPI_STORE, out=x0.clone() if resid else None, **kw)
+    x, planes, stats, slots = ops.gemm_ln(a_s, w_s, b, tab, ops.EPI_RESIDUAL_LN if resid else ops.EPI_STORE_LN,
+                                          out=x0.clone() if resid else None, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(x, plain), f"fp32 rows differ from the plain epilogue: max {(x - plain).abs().max().item():.3e}"
+    want_planes = ops.split_planes(x, fmt) if fmt == ops.FMT_F16F8 else ops.split_bf16(x)
+    assert torch.equal(planes.view(torch.int16), want_planes.view(torch.int16)), "planes are not the split of the stored rows"
+    assert 1 <= slots <= 8 and torch.all(stats[:, slots:] == 0)
+    s = stats[:, :slots].double().sum(1)
+    xd = x.double()
+    assert (s[:, 0] - xd.sum(1)).abs().max().item() < 1e-4 * max(1.0, xd.abs().sum(1).max().item()) * 1e-1
+    assert ((s[:, 1] - (xd * xd).sum(1)).abs() / (xd * xd).sum(1)).max().item() < 5e-6
+    # bit-reproducible statistics: a second launch with another M (another tile schedule) gives the same bits for the shared rows
+    m2 = m - 37
+    x2, _, stats2, _ = ops.gemm_ln(a_s[:, :m2].contiguous(), w_s, b, tab, ops.EPI_RESIDUAL_LN if resid else ops.EPI_STORE_LN,
+                                   out=x0[:m2].clone() if resid else None, **kw)
+    assert torch.equal(x2, x[:m2]) and torch.equal(stats2, stats[:m2])
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3", "simt"])
+@pytest.mark.parametrize("epilogue", [ops.EPI_STORE, ops.EPI_GELU, ops.EPI_STORE_SPLIT])
+@pytest.mark.parametrize("m,d,n", [(101 * 6, 576, 1728), (515, 288, 1152), (300, 144, 576)])
+def test_gemm_ln_consumer_matches_layernorm_then_linear(precision, epilogue, m, d, n):
+    """LayerNorm folded into its consumer GEMM (qkv, fc1): raw-x planes + W * diag(gamma) + the statistics written by a producer
+    epilogue give LayerNorm(x) W^T + b within the operand format's error bound (fp64 reference of the unfolded formula)."""
+    g = torch.Generator(device=DEV).manual_seed(m + n)
+    gamma = 1 + 0.1 * torch.randn(d, generator=g, device=DEV)
+    beta = 0.1 * torch.randn(d, generator=g, device=DEV)
+    w = torch.randn((n, d), generator=g, device=DEV) * 0.05
+    b = torch.randn(n, generator=g, device=DEV) * 0.1
+    # x with a row-dependent offset and scale, produced by a *_LN epilogue (identity-like GEMM would do; use a real one)
+    a0 = torch.randn((m, 64), generator=g, device=DEV)
+    w0 = torch.randn((d, 64), generator=g, device=DEV) * 0.3
+    x0 = (torch.randn((m, d), generator=g, device=DEV) * (0.5 + torch.rand((m, 1), generator=g, device=DEV) * 3)
+          + torch.randn((m, 1), generator=g, device=DEV))
+    fmt = ops.plane_format(precision)
+    kw = dict(precision=precision)
+    wg = w * gamma[None, :]
+    if precision == "f16f8":
+        t0 = ops.weight_log2_scale(float(w0.abs().max().item()))
+        x, xa, stats, slots = ops.gemm_ln(ops.split_planes(a0, fmt), ops.split_planes(w0, fmt, w_role=True, log2_scale=t0), None, None,
+                                          ops.EPI_RESIDUAL_LN, out=x0.clone(), precision=precision, w_log2_scale=t0 + 8)
+        t = ops.weight_log2_scale(float(wg.abs().max().item()))
+        w_s = ops.split_planes(wg, fmt, w_role=True, log2_scale=t)
+        kw["w_log2_scale"] = t + 8
+    else:
+        x, xa, stats, slots = ops.gemm_ln(ops.split_bf16(a0), ops.split_bf16(w0), None, None, ops.EPI_RESIDUAL_LN, out=x0.clone(),
+                                          precision=precision)
+        w_s = ops.split_bf16(wg)
+    c1 = wg.double().sum(1).float()
+    c2 = (b.double() + w.double() @ beta.double()).float()
+    got = ops.gemm_ln(xa, w_s, c2, None, epilogue, stats_in=stats, c1=c1, slots_in=slots, **kw)
+    torch.cuda.synchronize()
+    xd = x.double()
+    ln = torch.nn.functional.layer_norm(xd, (d,), gamma.double(), beta.double(), 1e-6)
+    ref = ln @ w.double().T + b.double()
+    rstd = 1.0 / torch.sqrt(xd.var(1, unbiased=False, keepdim=True) + 1e-6)
+    bound = rstd * (xd.abs() @ wg.double().abs().T) + 1.0        # the contraction runs on raw x: its error scales with rstd * sum |x||W'|
+    if epilogue == ops.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+        got = _planes_value(got, "f16f8" if precision == "f16f8" else "bf16x3")
+    elif epilogue == ops.EPI_STORE_SPLIT:
+        got = _unsplit(got)
+    else:
+        got = got.double()
+    rel = ((got - ref).abs() / bound).max().item()
+    print(f"ln-fold consumer {precision} epi {epilogue} M={m} D={d} N={n}: max|err|={(got - ref).abs().max().item():.3e} rel-to-bound={rel:.3e}")
+    assert rel < {"f16f8": 2.0 ** -13, "bf16x3": 3e-5, "simt": 1e-5}[precision]
+
+
 def test_f16f8_activation_planes():
     """LayerNorm / attention outputs in the f16f8 A-role format decode to the fp32 value within 2^-15 relative."""
     g = torch.Generator(device=DEV).manual_seed(11)
@@ -243,6 +339,31 @@ def test_engine_packs_every_precision_on_demand():
         assert torch.equal(eng.forward(x, precision=prec), engine.VitEngine("nerve_cell", sd, DEV, precision=prec).forward(x))
     with pytest.raises(KeyError):
         eng.forward(x, precision="fp8")
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3", "simt"])
+@pytest.mark.parametrize("panel", ["immune_full", "immune_base", "nerve_cell"])
+def test_vit_layernorm_fold_masks_agree(panel, precision, monkeypatch):
+    """RIBCA_LN_FOLD: 0 = LayerNorm kernels, 1 = norm1 inside the qkv GEMM (default), 3 = norm1 and norm2 inside qkv / fc1.
+    The same network in the three schedules: probabilities within the operand format's error of each other and of the
+    fp64-accurate fp32 path (the folded contraction runs on raw x and W * diag(gamma) instead of on LayerNorm(x) and W)."""
+    sd, _ = _vit_pair(panel, seed=11)
+    spec = weights.VIT_SPECS[panel]
+    x = torch.rand((150, spec.in_chans, 40, 40), device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    out = {}
+    for mask in (0, 1, 3):
+        monkeypatch.setenv("RIBCA_LN_FOLD", str(mask))
+        eng = engine.VitEngine(panel, sd, DEV, precision=precision)
+        assert eng.ln_fold == mask and eng.desc.ln_folded == mask
+        out[mask] = eng.forward(x)
+        if mask == 0:
+            exact = eng.forward(x, precision="fp32")        # plain fp32 FMA path (never folded)
+    tol = {"f16f8": 4e-4, "bf16x3": 1.5e-4, "simt": 5e-5}[precision]
+    for mask in (0, 1, 3):
+        d = (out[mask] - exact).abs().max().item()
+        print(f"{panel} {precision} fold mask {mask}: max|dprob| vs fp32 path {d:.3e}")
+        assert d < tol
+    assert not torch.equal(out[0], out[1])                  # the folded schedule really is another computation
 
 
 @pytest.mark.parametrize("n", [512, 777, 1300])
