@@ -18,6 +18,7 @@
 // inside the 128 x TP tile hold the next cell's tokens (or TMA zero fill); they are masked and never stored.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace ribca {
 
@@ -343,15 +344,241 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-static int make_qkv_map(CUtensorMap* map, const void* base, long long plane_elems, long long rows, int width, int box_rows) {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// head_dim 48 (vit_l, the headline classifier): THREE item groups per CTA.
+// The kernel above is bound by the serial chain of one (cell, head) item per group (TMA -> S MMA -> softmax -> PV MMA ->
+// output, ~5 us) with only two items in flight per SM: DRAM at 56 % and the tensor pipe at 18 % (profiles/r01h_summary.md).
+// A third item needs shared memory: the 128-byte-wide Q / K / V boxes hold 96 bytes of head each.  Here Q and K are staged
+// without padding as TWO tiles per plane - 32 columns (64-byte rows, SWIZZLE_64B: K steps 0, 1) + 16 columns (32-byte rows,
+// SWIZZLE_32B: K step 2) - 21 KB per operand instead of 28 KB; V keeps its 128-byte MN-major tile (its last 16 columns belong to
+// the next head and are never read: N = 48).  The O staging tile of the TMA store lives in the V tiles, which are dead once the
+// PV MMAs retire; the next V load is issued after that store has read them (by the MMA-issuing thread, right after it has
+// issued the next S).  Slot = 70 KB, three slots = 210 KB; TMEM: 160 columns per group (S / P 112, O 48).
+// One thread per query row (128 threads per group, 384 per CTA).
+constexpr int kAtt3Threads = 384;
+constexpr int kA3TP = 112;
+constexpr int kA3T64 = kA3TP * 64;                   // 32-column tile of one plane
+constexpr int kA3T32 = kA3TP * 32;                   // 16-column tile
+constexpr int kA3V = kA3TP * 128;                    // V tile of one plane
+constexpr int kA3Slot = 4 * kA3T64 + 2 * kA3V + 4 * kA3T32;
+constexpr int kA3Smem = 3 * kA3Slot + 1024 + 256;
+static_assert(kA3Slot % 1024 == 0 && kA3T64 % 512 == 0 && kA3T32 % 256 == 0, "tile alignment of the swizzle modes");
+
+// K-major, 32-byte swizzle (16 bf16 per row): 8-row groups are 256 B apart, layout type 6 (SWIZZLE_32B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+__device__ __forceinline__ void group128_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+template <int FMT>
+__global__ void __launch_bounds__(kAtt3Threads, 1)
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_constant__ CUtensorMap tmap_32,
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
+  constexpr int TP = kA3TP, HD = 48;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kA3Slot);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = tid >> 7;                  // item group = slot (4 warps: TMEM lane quadrants 0..3)
+  const int row = tid & 127;                 // query row owned by this thread
+  const bool leader = row == 0;
+  uint64_t* bar_qk = bars + 4 * grp;         // TMA  -> S MMA
+  uint64_t* bar_v = bar_qk + 1;              // TMA  -> PV MMA
+  uint64_t* bar_s = bar_qk + 2;              // S done  -> softmax, Q / K reload
+  uint64_t* bar_o = bar_qk + 3;              // PV done -> output
+  if (tid == 0) {
+    prefetch_tmap(&tmap_64);
+    prefetch_tmap(&tmap_32);
+    prefetch_tmap(&tmap_v);
+    prefetch_tmap(&tmap_out);
+    for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+  const uint32_t tmem_sp = tmem_base + grp * 160;          // S (fp32, 112 cols); later P_hi at +0, P_lo at +56 (bf16x2, 56 cols each)
+  const uint32_t tmem_o = tmem_sp + 112;                   // O (fp32, 48 cols)
+
+  uint8_t* slot = smem + grp * kA3Slot;
+  uint8_t* q64[2] = {slot, slot + kA3T64};
+  uint8_t* k64[2] = {slot + 2 * kA3T64, slot + 3 * kA3T64};
+  uint8_t* v_s[2] = {slot + 4 * kA3T64, slot + 4 * kA3T64 + kA3V};
+  uint8_t* t32 = slot + 4 * kA3T64 + 2 * kA3V;
+  uint8_t* q32[2] = {t32, t32 + kA3T32};
+  uint8_t* k32[2] = {t32 + 2 * kA3T32, t32 + 3 * kA3T32};
+  uint8_t* o_s = v_s[0];                     // [2 planes][tokens rows][48] bf16, dense: the TMA store's source, in the dead V tiles
+
+  const uint32_t idesc_s = make_instr_desc(128, TP, false);
+  const uint32_t idesc_o = make_instr_desc(128, HD, true);
+  const int n_items = p.cells * p.heads;
+  const int first = blockIdx.x * 3 + grp, stride = 3 * gridDim.x;
+  const int my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+
+  auto load_qk = [&](int item) {
+    const int cell = item / p.heads, head = item - cell * p.heads;
+    const int row0 = cell * p.tokens;
+    mbar_expect_tx(bar_qk, 4u * kA3T64 + 4u * kA3T32);
+    for (int pl = 0; pl < 2; ++pl) {
+      tma_load_3d(q64[pl], &tmap_64, bar_qk, head * HD, row0, pl);
+      tma_load_3d(k64[pl], &tmap_64, bar_qk, (p.heads + head) * HD, row0, pl);
+      tma_load_3d(q32[pl], &tmap_32, bar_qk, head * HD + 32, row0, pl);
+      tma_load_3d(k32[pl], &tmap_32, bar_qk, (p.heads + head) * HD + 32, row0, pl);
+    }
+  };
+  auto load_v = [&](int item) {
+    const int cell = item / p.heads, head = item - cell * p.heads;
+    mbar_expect_tx(bar_v, 2u * kA3V);
+    for (int pl = 0; pl < 2; ++pl) tma_load_3d(v_s[pl], &tmap_v, bar_v, (2 * p.heads + head) * HD, cell * p.tokens, pl);
+  };
+
+  if (leader && my_items > 0) { load_qk(first); load_v(first); }
+  uint32_t ph = 0;
+  for (int k = 0; k < my_items; ++k, ph ^= 1u) {
+    const int item = first + k * stride;
+    const int cell = item / p.heads, head = item - cell * p.heads;
+    // ---- S = Q K^T ------------------------------------------------------------------------------------
+    if (leader) {
+      mbar_wait(bar_qk, ph);
+      tcgen05_fence_after();
+      const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};       // lo.hi, hi.lo, hi.hi
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t qa = smem_u32(q64[pa[ps]]), kb = smem_u32(k64[pb[ps]]);
+        umma_bf16(tmem_sp, make_smem_desc_sw64(qa), make_smem_desc_sw64(kb), idesc_s, acc);
+        umma_bf16(tmem_sp, make_smem_desc_sw64(qa + 32), make_smem_desc_sw64(kb + 32), idesc_s, 1u);
+        umma_bf16(tmem_sp, make_smem_desc_sw32(smem_u32(q32[pa[ps]])), make_smem_desc_sw32(smem_u32(k32[pb[ps]])), idesc_s, 1u);
+        acc = 1;
+      }
+      umma_commit(bar_s);
+      if (k > 0) {
+        // the previous item's output store has read the V tiles (its staging): only now may this item's V land there
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        load_v(item);
+      }
+    }
+    mbar_wait(bar_s, ph);
+    tcgen05_fence_after();
+    if (leader && k + 1 < my_items) load_qk(item + stride);     // Q / K tiles are dead: prefetch the next item
+    // ---- softmax of this thread's row; P -> TMEM over S -----------------------------------------------
+    float s[TP];
+#pragma unroll
+    for (int c = 0; c < TP / 16; ++c) tmem_ld16_nowait(tmem_sp + lane_addr + c * 16, reinterpret_cast<uint32_t*>(s) + c * 16);
+    tmem_ld_wait();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+      if (j >= 96 && j >= p.tokens) s[j] = -INFINITY;         // only the tail chunk can be out of range (96 < tokens <= 112)
+      mx = fmaxf(mx, s[j]);
+    }
+    const float off = mx * p.scale_log2e;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < TP; j += 2) {
+      s[j] = fast_exp2(fmaf(s[j], p.scale_log2e, -off));       // exp((s - max) / sqrt(hd)); 0 for masked columns
+      s[j + 1] = fast_exp2(fmaf(s[j + 1], p.scale_log2e, -off));
+      sum0 += s[j];
+      sum1 += s[j + 1];
+    }
+    // every S value of the row is in registers: P may overwrite S (this thread's own TMEM lane only)
+#pragma unroll
+    for (int c = 0; c < TP / 16; ++c) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_bf16x2(s[c * 16 + 2 * e], s[c * 16 + 2 * e + 1], hi[e], lo[e]);
+      tmem_st8(tmem_sp + lane_addr + c * 8, hi);
+      tmem_st8(tmem_sp + lane_addr + 56 + c * 8, lo);
+    }
+    tmem_st_wait();
+    tcgen05_fence_before();
+    group128_sync(grp);
+    // ---- O = P V --------------------------------------------------------------------------------------
+    if (leader) {
+      tcgen05_fence_after();
+      mbar_wait(bar_v, ph);
+      tcgen05_fence_after();
+      const uint32_t pa[3] = {56, 0, 0};                      // P_lo, P_hi, P_hi
+      const int pb[3] = {0, 1, 0};                            // V_hi, V_lo, V_hi
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t vb = smem_u32(v_s[pb[ps]]);
+#pragma unroll
+        for (int kk = 0; kk < TP / 16; ++kk) {
+          umma_bf16_ts(tmem_o, tmem_sp + pa[ps] + kk * 8, make_smem_desc_mn(vb + kk * 2048), idesc_o, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tcgen05_fence_after();
+    // ---- normalise, split, stage in the (dead) V tiles, one TMA store per item ------------------------------------
+    {
+      const float inv = 1.0f / (sum0 + sum1);
+      float o[HD];
+#pragma unroll
+      for (int c = 0; c < HD / 16; ++c) tmem_ld16_nowait(tmem_o + lane_addr + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
+      tmem_ld_wait();
+      if (row < p.tokens) {
+        uint8_t* dh = o_s + row * (HD * 2);
+        uint8_t* dl = o_s + p.tokens * (HD * 2) + row * (HD * 2);
+#pragma unroll
+        for (int ch = 0; ch < HD / 8; ++ch) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, FMT, h[e], l[e]);
+          *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      group128_sync(grp);                    // also: every thread's TMEM reads of O / P are done before the next item's MMAs
+      if (leader) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * HD), "r"(cell * p.tokens), "r"(0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// box of `box_cols` columns (64 / 32 / 16: one 128- / 64- / 32-byte swizzle row) x box_rows rows of one plane
+static int make_qkv_map(CUtensorMap* map, const void* base, long long plane_elems, long long rows, int width, int box_rows,
+                        int box_cols = 64) {
   auto encode = tensor_map_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return RIBCA_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)plane_elems * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return RIBCA_ECUDA; }
   return RIBCA_OK;
@@ -381,6 +608,13 @@ static int launch_tc_hdp(const CUtensorMap& mq, const CUtensorMap& mkv, const CU
     case 64: return launch_tc<TP, 64, FMT>(mq, mkv, mo, p, hi, lo, st);
     default: set_error("attention_tc: unsupported padded head_dim %d", p.hdp); return RIBCA_EUNSUPPORTED;
   }
+}
+
+// RIBCA_ATTN3=0 keeps the two-group kernel for head_dim 48 (A/B)
+static bool three_groups_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RIBCA_ATTN3"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
 }
 
 // qkv_split: [2][M][3*heads*hdp] bf16, plane stride qkv_plane elements; out_split [2][M][heads*hd]
@@ -414,6 +648,26 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
   }
   bf16* hi = static_cast<bf16*>(out_split);
   bf16* lo = hi + out_plane;
+  if (hd == 48 && tokens > 96 && three_groups_enabled()) {
+    // vit_l: three item groups per CTA, unpadded Q / K tiles (attention_tc3_kernel)
+    CUtensorMap m64, m32;
+    RIBCA_TRY(make_qkv_map(&m64, qkv_split, qkv_plane, M, width, TP, 32));
+    RIBCA_TRY(make_qkv_map(&m32, qkv_split, qkv_plane, M, width, TP, 16));
+    const int grid = std::min((cells * heads + 2) / 3, num_sms());
+    const bool prof = profiling();
+    if (out_fmt == kFmtF16F8) {
+      RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc3_kernel<kFmtF16F8>), kA3Smem, "cudaFuncSetAttribute(attention_tc3_kernel)"));
+      if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * hd, st);
+      attention_tc3_kernel<kFmtF16F8><<<grid, kAtt3Threads, kA3Smem, st>>>(m64, m32, mkv, mo, p);
+    } else {
+      RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc3_kernel<kFmtBf16>), kA3Smem, "cudaFuncSetAttribute(attention_tc3_kernel)"));
+      if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * hd, st);
+      attention_tc3_kernel<kFmtBf16><<<grid, kAtt3Threads, kA3Smem, st>>>(m64, m32, mkv, mo, p);
+    }
+    if (prof) prof_end_span(st);
+    RIBCA_LAUNCH_CHECK("attention_tc3_kernel");
+    return RIBCA_OK;
+  }
   return out_fmt == kFmtF16F8 ? launch_tc_hdp<TP, kFmtF16F8>(mq, mkv, mo, p, hi, lo, st)
                               : launch_tc_hdp<TP, kFmtBf16>(mq, mkv, mo, p, hi, lo, st);
 }

@@ -285,7 +285,7 @@ def test_layernorm_and_attention_vs_torch():
 
 
 @pytest.mark.parametrize("cells,tokens,heads,hd", [(3, 101, 12, 48), (2, 101, 12, 12), (4, 101, 12, 24), (2, 101, 12, 32),
-                                                   (3, 101, 12, 64), (2, 40, 4, 16), (1, 112, 2, 64), (5, 97, 3, 48), (300, 101, 12, 48)])
+                                                   (3, 101, 12, 64), (2, 40, 4, 16), (1, 112, 2, 64), (5, 97, 3, 48), (300, 101, 12, 48), (2, 112, 12, 48), (7, 100, 5, 48)])
 def test_attention_tensor_core_vs_torch(cells, tokens, heads, hd):
     g = torch.Generator(device=DEV).manual_seed(cells * 1000 + tokens + hd)
     m, hdp = cells * tokens, (hd + 15) // 16 * 16
