@@ -65,6 +65,9 @@ constexpr int kATile = BM * BK * 2;             // one plane of A:  16 KB at BK 
 constexpr int kABytes = 2 * kATile;             // both planes:    32 KB
 constexpr int kBBytesMax = 2 * (kMaxBN / 2) * BK * 2; // this CTA's half of W, both planes: 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
+#ifndef RIBCA_MMA_ORDER
+#define RIBCA_MMA_ORDER 0       // f16f8: 0 = e4m3 / fp16 instructions alternate per 16 elements, 1 = K block in e4m3, then in fp16
+#endif
 #ifndef RIBCA_FORCE_CW16
 #define RIBCA_FORCE_CW16 0
 #endif
@@ -583,6 +586,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (shp.fmt == kFmtF16F8) {
             // e4m3 pair planes (both correction terms, K doubled: 32 bytes = one K = 32 instruction per 16 elements)
             // then the fp16 planes; one accumulator, one instruction descriptor (format code 0 = E4M3 = F16)
+#if RIBCA_MMA_ORDER == 1
+            // A/B variant: the whole K block in e4m3, then the whole K block in fp16 (profiles/r02_gemm_order.md)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_e4m3_2sm(d_tmem, make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2), make_smem_desc_k(b_addr + w_tile + k * UMMA_K * 2),
+                            idesc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_2sm(d_tmem, make_smem_desc_k(a_addr + k * UMMA_K * 2), make_smem_desc_k(b_addr + k * UMMA_K * 2), idesc, 1u);
+#else
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t a_0 = make_smem_desc_k(a_addr + k * UMMA_K * 2);
@@ -592,6 +605,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               umma_e4m3_2sm(d_tmem, a_1, w_1, idesc, (it > 0 || k > 0) ? 1u : 0u);
               umma_bf16_2sm(d_tmem, a_0, w_0, idesc, 1u);
             }
+#endif
           } else if (shp.n_planes == 2) {
             // lo.hi + hi.lo + hi.hi from the four staged tiles
 #pragma unroll

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 k=$1; shift
 timeout 400 python -m pytest tests/test_gpu_networks.py -q -m gpu -k "$k" -p no:cacheprovider -x 2>&1 | tail -4
-python bench.py --steps 2 --warmup 2 --no-cpu-baseline "$@" > gpurun_out/bench_q.json 2>gpurun_out/bench_q.err
+python bench.py --steps 2 --warmup 2 --quick "$@" > gpurun_out/bench_q.json 2>gpurun_out/bench_q.err
 python - <<'PY'
 import json
 try:

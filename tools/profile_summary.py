@@ -20,7 +20,7 @@ try:
         agg[name][0] += 1; agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
     emit(f"# {tag}: ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, "
-         "`bench.py --size 1024 --steps 1 --warmup 1 --no-cpu-baseline`; cold-cache serialised times: compare SHARES)\n")
+         "`bench.py --size 1024 --steps 1 --warmup 1 --quick`; cold-cache serialised times: compare SHARES)\n")
     emit("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
         emit(f"| {k[:70]} | {v[0]} | {v[1]:.2f} | {100 * v[1] / tot:.1f}% |")
