@@ -346,24 +346,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// head_dim 48 (vit_l, the headline classifier): THREE item groups per CTA.
+// head_dim 24 / 32 / 48 (every classifier but nerve_cell; 48 = vit_l, the headline): THREE item groups per CTA.
 // The kernel above is bound by the serial chain of one (cell, head) item per group (TMA -> S MMA -> softmax -> PV MMA ->
 // output, ~5 us) with only two items in flight per SM: DRAM at 56 % and the tensor pipe at 18 % (profiles/r01h_summary.md).
-// A third item needs shared memory: the 128-byte-wide Q / K / V boxes hold 96 bytes of head each.  Here Q and K are staged
-// without padding as TWO tiles per plane - 32 columns (64-byte rows, SWIZZLE_64B: K steps 0, 1) + 16 columns (32-byte rows,
-// SWIZZLE_32B: K step 2) - 21 KB per operand instead of 28 KB; V keeps its 128-byte MN-major tile (its last 16 columns belong to
-// the next head and are never read: N = 48).  The O staging tile of the TMA store lives in the V tiles, which are dead once the
-// PV MMAs retire; the next V load is issued after that store has read them (by the MMA-issuing thread, right after it has
-// issued the next S).  Slot = 70 KB, three slots = 210 KB; TMEM: 160 columns per group (S / P 112, O 48).
-// One thread per query row (128 threads per group, 384 per CTA).
+// A third item needs shared memory: the 128-byte-wide Q / K / V boxes hold 96 (or 64) bytes of head each.  Here Q and K are
+// staged without padding: 32 columns as one tile of 64-byte rows (SWIZZLE_64B: K steps 0, 1) and, for head_dim 48, 16 more
+// as a tile of 32-byte rows (SWIZZLE_32B: K step 2) - 21 KB (14 KB) per operand instead of 28 KB; V keeps its 128-byte
+// MN-major tile (its last columns belong to the next head and are never read: N = head_dim).  The O staging tile of the TMA
+// store lives in the V tiles, which are dead once the PV MMAs retire; the next V load is issued after that store has read
+// them (by the MMA-issuing thread, right after it has issued the next S).  Slot = 70 KB (56 KB), three slots = 210 KB;
+// TMEM: 160 columns per group (S / P 112, O <= 48).  One thread per query row (128 threads per group, 384 per CTA).
+// 4096 cells x 12 heads of vit_l: 0.773 -> 0.683 ms = 5.58 TB/s algorithmic, 85 % of the HBM copy peak (profiles/r02_attention.md).
 constexpr int kAtt3Threads = 384;
 constexpr int kA3TP = 112;
 constexpr int kA3T64 = kA3TP * 64;                   // 32-column tile of one plane
 constexpr int kA3T32 = kA3TP * 32;                   // 16-column tile
 constexpr int kA3V = kA3TP * 128;                    // V tile of one plane
-constexpr int kA3Slot = 4 * kA3T64 + 2 * kA3V + 4 * kA3T32;
-constexpr int kA3Smem = 3 * kA3Slot + 1024 + 256;
-static_assert(kA3Slot % 1024 == 0 && kA3T64 % 512 == 0 && kA3T32 % 256 == 0, "tile alignment of the swizzle modes");
+__host__ __device__ constexpr int a3_slot_bytes(int hdp) { return 4 * kA3T64 + 2 * kA3V + (hdp == 48 ? 4 * kA3T32 : 0); }
+__host__ __device__ constexpr int a3_smem_bytes(int hdp) { return 3 * a3_slot_bytes(hdp) + 1024 + 256; }
+static_assert(a3_slot_bytes(48) % 1024 == 0 && a3_slot_bytes(32) % 1024 == 0 && kA3T64 % 512 == 0 && kA3T32 % 256 == 0,
+              "tile alignment of the swizzle modes");
 
 // K-major, 32-byte swizzle (16 bf16 per row): 8-row groups are 256 B apart, layout type 6 (SWIZZLE_32B)
 __device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
@@ -377,14 +379,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
 }
 __device__ __forceinline__ void group128_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
-template <int FMT>
+template <int HDP, int FMT>
 __global__ void __launch_bounds__(kAtt3Threads, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_constant__ CUtensorMap tmap_32,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
-  constexpr int TP = kA3TP, HD = 48;
+  static_assert(HDP == 32 || HDP == 48, "Q / K pieces: 32 columns (+ 16 for head_dim 48)");
+  constexpr int TP = kA3TP;
+  constexpr bool kPiece32 = HDP == 48;
+  constexpr int kSlot = a3_slot_bytes(HDP);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kA3Slot);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kSlot);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -397,7 +402,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
   uint64_t* bar_o = bar_qk + 3;              // PV done -> output
   if (tid == 0) {
     prefetch_tmap(&tmap_64);
-    prefetch_tmap(&tmap_32);
+    if (kPiece32) prefetch_tmap(&tmap_32);
     prefetch_tmap(&tmap_v);
     prefetch_tmap(&tmap_out);
     for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
@@ -410,19 +415,19 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   const uint32_t tmem_sp = tmem_base + grp * 160;          // S (fp32, 112 cols); later P_hi at +0, P_lo at +56 (bf16x2, 56 cols each)
-  const uint32_t tmem_o = tmem_sp + 112;                   // O (fp32, 48 cols)
+  const uint32_t tmem_o = tmem_sp + 112;                   // O (fp32, HDP cols)
 
-  uint8_t* slot = smem + grp * kA3Slot;
+  uint8_t* slot = smem + grp * kSlot;
   uint8_t* q64[2] = {slot, slot + kA3T64};
   uint8_t* k64[2] = {slot + 2 * kA3T64, slot + 3 * kA3T64};
   uint8_t* v_s[2] = {slot + 4 * kA3T64, slot + 4 * kA3T64 + kA3V};
   uint8_t* t32 = slot + 4 * kA3T64 + 2 * kA3V;
   uint8_t* q32[2] = {t32, t32 + kA3T32};
   uint8_t* k32[2] = {t32 + 2 * kA3T32, t32 + 3 * kA3T32};
-  uint8_t* o_s = v_s[0];                     // [2 planes][tokens rows][48] bf16, dense: the TMA store's source, in the dead V tiles
+  uint8_t* o_s = v_s[0];                     // [2 planes][tokens rows][hd] bf16, dense: the TMA store's source, in the dead V tiles
 
   const uint32_t idesc_s = make_instr_desc(128, TP, false);
-  const uint32_t idesc_o = make_instr_desc(128, HD, true);
+  const uint32_t idesc_o = make_instr_desc(128, HDP, true);
   const int n_items = p.cells * p.heads;
   const int first = blockIdx.x * 3 + grp, stride = 3 * gridDim.x;
   const int my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
@@ -430,18 +435,20 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
   auto load_qk = [&](int item) {
     const int cell = item / p.heads, head = item - cell * p.heads;
     const int row0 = cell * p.tokens;
-    mbar_expect_tx(bar_qk, 4u * kA3T64 + 4u * kA3T32);
+    mbar_expect_tx(bar_qk, 4u * kA3T64 + (kPiece32 ? 4u * kA3T32 : 0u));
     for (int pl = 0; pl < 2; ++pl) {
-      tma_load_3d(q64[pl], &tmap_64, bar_qk, head * HD, row0, pl);
-      tma_load_3d(k64[pl], &tmap_64, bar_qk, (p.heads + head) * HD, row0, pl);
-      tma_load_3d(q32[pl], &tmap_32, bar_qk, head * HD + 32, row0, pl);
-      tma_load_3d(k32[pl], &tmap_32, bar_qk, (p.heads + head) * HD + 32, row0, pl);
+      tma_load_3d(q64[pl], &tmap_64, bar_qk, head * HDP, row0, pl);
+      tma_load_3d(k64[pl], &tmap_64, bar_qk, (p.heads + head) * HDP, row0, pl);
+      if (kPiece32) {
+        tma_load_3d(q32[pl], &tmap_32, bar_qk, head * HDP + 32, row0, pl);
+        tma_load_3d(k32[pl], &tmap_32, bar_qk, (p.heads + head) * HDP + 32, row0, pl);
+      }
     }
   };
   auto load_v = [&](int item) {
     const int cell = item / p.heads, head = item - cell * p.heads;
     mbar_expect_tx(bar_v, 2u * kA3V);
-    for (int pl = 0; pl < 2; ++pl) tma_load_3d(v_s[pl], &tmap_v, bar_v, (2 * p.heads + head) * HD, cell * p.tokens, pl);
+    for (int pl = 0; pl < 2; ++pl) tma_load_3d(v_s[pl], &tmap_v, bar_v, (2 * p.heads + head) * HDP, cell * p.tokens, pl);
   };
 
   if (leader && my_items > 0) { load_qk(first); load_v(first); }
@@ -460,7 +467,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
         const uint32_t qa = smem_u32(q64[pa[ps]]), kb = smem_u32(k64[pb[ps]]);
         umma_bf16(tmem_sp, make_smem_desc_sw64(qa), make_smem_desc_sw64(kb), idesc_s, acc);
         umma_bf16(tmem_sp, make_smem_desc_sw64(qa + 32), make_smem_desc_sw64(kb + 32), idesc_s, 1u);
-        umma_bf16(tmem_sp, make_smem_desc_sw32(smem_u32(q32[pa[ps]])), make_smem_desc_sw32(smem_u32(k32[pb[ps]])), idesc_s, 1u);
+        if (kPiece32)
+          umma_bf16(tmem_sp, make_smem_desc_sw32(smem_u32(q32[pa[ps]])), make_smem_desc_sw32(smem_u32(k32[pb[ps]])), idesc_s, 1u);
         acc = 1;
       }
       umma_commit(bar_s);
@@ -529,20 +537,23 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
     // ---- normalise, split, stage in the (dead) V tiles, one TMA store per item ------------------------------------
     {
       const float inv = 1.0f / (sum0 + sum1);
-      float o[HD];
+      float o[HDP];
 #pragma unroll
-      for (int c = 0; c < HD / 16; ++c) tmem_ld16_nowait(tmem_o + lane_addr + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
+      for (int c = 0; c < HDP / 16; ++c) tmem_ld16_nowait(tmem_o + lane_addr + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
       tmem_ld_wait();
       if (row < p.tokens) {
-        uint8_t* dh = o_s + row * (HD * 2);
-        uint8_t* dl = o_s + p.tokens * (HD * 2) + row * (HD * 2);
+        const int row_b = p.hd * 2;
+        uint8_t* dh = o_s + row * row_b;
+        uint8_t* dl = o_s + p.tokens * row_b + row * row_b;
 #pragma unroll
-        for (int ch = 0; ch < HD / 8; ++ch) {
-          uint32_t h[4], l[4];
+        for (int ch = 0; ch < HDP / 8; ++ch) {
+          if (ch * 8 < p.hd) {
+            uint32_t h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, FMT, h[e], l[e]);
-          *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, FMT, h[e], l[e]);
+            *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -550,7 +561,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
       group128_sync(grp);                    // also: every thread's TMEM reads of O / P are done before the next item's MMAs
       if (leader) {
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                     ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * HD), "r"(cell * p.tokens), "r"(0)
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * p.hd), "r"(cell * p.tokens), "r"(0)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -565,6 +576,20 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int HDP, int FMT>
+static int launch_tc3(const CUtensorMap& m64, const CUtensorMap& m32, const CUtensorMap& mv, const CUtensorMap& mo, const AttnParams& p,
+                      cudaStream_t st) {
+  constexpr int kSmem = a3_smem_bytes(HDP);
+  RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc3_kernel<HDP, FMT>), kSmem, "cudaFuncSetAttribute(attention_tc3_kernel)"));
+  const int grid = std::min((p.cells * p.heads + 2) / 3, num_sms());
+  const bool prof = profiling();
+  if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)p.cells * p.heads * (double)p.tokens * p.tokens * p.hd, st);
+  attention_tc3_kernel<HDP, FMT><<<grid, kAtt3Threads, kSmem, st>>>(m64, m32, mv, mo, p);
+  if (prof) prof_end_span(st);
+  RIBCA_LAUNCH_CHECK("attention_tc3_kernel");
+  return RIBCA_OK;
 }
 
 // box of `box_cols` columns (64 / 32 / 16: one 128- / 64- / 32-byte swizzle row) x box_rows rows of one plane
@@ -610,7 +635,7 @@ static int launch_tc_hdp(const CUtensorMap& mq, const CUtensorMap& mkv, const CU
   }
 }
 
-// RIBCA_ATTN3=0 keeps the two-group kernel for head_dim 48 (A/B)
+// RIBCA_ATTN3=0 keeps the two-group kernel for head_dim 24 / 32 / 48 (A/B)
 static bool three_groups_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RIBCA_ATTN3"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -648,25 +673,13 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
   }
   bf16* hi = static_cast<bf16*>(out_split);
   bf16* lo = hi + out_plane;
-  if (hd == 48 && tokens > 96 && three_groups_enabled()) {
-    // vit_l: three item groups per CTA, unpadded Q / K tiles (attention_tc3_kernel)
+  if ((p.hdp == 48 || p.hdp == 32) && hd % 8 == 0 && tokens > 96 && three_groups_enabled()) {
+    // head_dim 24 / 32 / 48: three item groups per CTA, unpadded Q / K tiles (attention_tc3_kernel)
     CUtensorMap m64, m32;
     RIBCA_TRY(make_qkv_map(&m64, qkv_split, qkv_plane, M, width, TP, 32));
     RIBCA_TRY(make_qkv_map(&m32, qkv_split, qkv_plane, M, width, TP, 16));
-    const int grid = std::min((cells * heads + 2) / 3, num_sms());
-    const bool prof = profiling();
-    if (out_fmt == kFmtF16F8) {
-      RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc3_kernel<kFmtF16F8>), kA3Smem, "cudaFuncSetAttribute(attention_tc3_kernel)"));
-      if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * hd, st);
-      attention_tc3_kernel<kFmtF16F8><<<grid, kAtt3Threads, kA3Smem, st>>>(m64, m32, mkv, mo, p);
-    } else {
-      RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc3_kernel<kFmtBf16>), kA3Smem, "cudaFuncSetAttribute(attention_tc3_kernel)"));
-      if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)cells * heads * (double)tokens * tokens * hd, st);
-      attention_tc3_kernel<kFmtBf16><<<grid, kAtt3Threads, kA3Smem, st>>>(m64, m32, mkv, mo, p);
-    }
-    if (prof) prof_end_span(st);
-    RIBCA_LAUNCH_CHECK("attention_tc3_kernel");
-    return RIBCA_OK;
+    if (p.hdp == 48) return out_fmt == kFmtF16F8 ? launch_tc3<48, kFmtF16F8>(m64, m32, mkv, mo, p, st) : launch_tc3<48, kFmtBf16>(m64, m32, mkv, mo, p, st);
+    return out_fmt == kFmtF16F8 ? launch_tc3<32, kFmtF16F8>(m64, m32, mkv, mo, p, st) : launch_tc3<32, kFmtBf16>(m64, m32, mkv, mo, p, st);
   }
   return out_fmt == kFmtF16F8 ? launch_tc_hdp<TP, kFmtF16F8>(mq, mkv, mo, p, hi, lo, st)
                               : launch_tc_hdp<TP, kFmtBf16>(mq, mkv, mo, p, hi, lo, st);
