@@ -19,7 +19,7 @@ import pandas as pd
 import torch
 
 from .. import ops
-from ..io import is_tiff, iter_tiff_planes, read_image, read_mask
+from ..io import is_npy, is_tiff, iter_npy_planes, iter_tiff_planes, read_image, read_mask
 from ..parallel import shard_range, world
 from .markerImputer import MarkerImputer
 
@@ -227,11 +227,12 @@ class ImageProcessor(object):
         rank, nranks = world()
         image_path = self.image_paths[i]
         img_dev = None
-        if self.normalization and nranks == 1 and is_tiff(image_path):
+        if self.normalization and nranks == 1 and (is_tiff(image_path) or is_npy(image_path)):
             try:                                          # decode, upload and stage 1 overlapped plane by plane
-                img_dev = ops.normalize_from_planes(iter_tiff_planes(image_path), self.device, self.blur, self.amax)
+                planes = iter_tiff_planes(image_path) if is_tiff(image_path) else iter_npy_planes(image_path)
+                img_dev = ops.normalize_from_planes(planes, self.device, self.blur, self.amax)
             except (ValueError, KeyError, struct.error, OSError):
-                img_dev = None                            # a TIFF flavour the reader does not take: whole-file decode below
+                img_dev = None                            # a file flavour the plane readers do not take: whole-file decode below
         if img_dev is not None:
             return img_dev
         image = read_image(image_path)

@@ -223,6 +223,33 @@ def iter_tiff_planes(path, pin: bool = True):
                 yield k * p0.samples + j, out
 
 
+def iter_npy_planes(path, pin: bool = True):
+    """The .npy counterpart of iter_tiff_planes: a C-ordered (C, H, W) / (H, W) array of a native numeric dtype is read plane by
+    plane with `readinto` into ONE (pinned) buffer; yields (k, stack) after plane k is complete.  Anything else (Fortran order,
+    object arrays, other ranks) raises ValueError and the caller falls back to np.load."""
+    with open(path, "rb") as f:
+        version = np.lib.format.read_magic(f)
+        shape, fortran, dtype = (np.lib.format.read_array_header_1_0 if version == (1, 0) else np.lib.format.read_array_header_2_0)(f)
+        if fortran or dtype.hasobject or len(shape) not in (2, 3) or not dtype.isnative or np.dtype(dtype).name not in (
+                "uint8", "uint16", "int32", "float32"):
+            raise ValueError(f"{path}: not a C-ordered uint8 / uint16 / int32 / float32 image stack")
+        c, h, w = shape if len(shape) == 3 else (1,) + tuple(shape)
+        out, _owner = _alloc((c, h, w), dtype, pin)
+        for k in range(c):
+            dst = memoryview(out[k]).cast("B")
+            got = 0
+            while got < len(dst):
+                n = f.readinto(dst[got:])
+                if not n:
+                    raise ValueError(f"{path}: truncated file")
+                got += n
+            yield k, out
+
+
+def is_npy(path) -> bool:
+    return str(path).lower().endswith(".npy")
+
+
 def is_tiff(path) -> bool:
     return str(path).lower().endswith((".tif", ".tiff", ".qptiff"))
 

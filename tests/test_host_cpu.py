@@ -355,3 +355,28 @@ def test_tiff_reader_property_random_layouts(tmp_path):
     open(path, "wb").write(blob[:8] + blob[8:60])          # header + part of the first strip, IFD gone
     with pytest.raises((ValueError, IOError, Exception)):
         bio.read_tiff_stack(path, pin=False)
+
+
+@pytest.mark.parametrize("dtype,shape", [("uint16", (3, 17, 9)), ("float32", (5, 4)), ("uint8", (2, 3, 3)), ("int32", (4, 8, 8))])
+def test_npy_plane_reader_streams_the_same_array(tmp_path, dtype, shape):
+    """io.iter_npy_planes (the .npy counterpart of iter_tiff_planes: readinto one buffer, a plane at a time) returns np.load's
+    array, yields every plane index once in order, and refuses layouts it cannot stream (the caller falls back to np.load)."""
+    from multiplexed_image_annotator_b200 import io
+    a = (np.random.default_rng(3).random(shape) * 200).astype(dtype)
+    path = str(tmp_path / "stack.npy")
+    np.save(path, a)
+    seen, out = [], None
+    for k, out in io.iter_npy_planes(path, pin=False):
+        seen.append(k)
+        assert np.array_equal(out[k], a[k] if a.ndim == 3 else a)        # plane k is complete when it is announced
+    assert seen == list(range(shape[0] if len(shape) == 3 else 1))
+    assert np.array_equal(out.reshape(a.shape), np.load(path))
+    for bad in (np.asfortranarray(np.zeros((2, 3, 4), np.float32)), np.zeros((2, 3, 4), np.float64), np.zeros((2, 2, 2, 2), np.uint8)):
+        np.save(path, bad)
+        with pytest.raises(ValueError):
+            list(io.iter_npy_planes(path, pin=False))
+    with open(path, "wb") as f:                                            # truncated payload
+        np.lib.format.write_array_header_1_0(f, {"descr": "<u2", "fortran_order": False, "shape": (2, 4, 4)})
+        f.write(b"\0" * 40)
+    with pytest.raises(ValueError):
+        list(io.iter_npy_planes(path, pin=False))
