@@ -267,3 +267,35 @@ def test_batch_csv_stays_inside_a_hard_memory_limit(tmp_path):
           f"budgeted run peaks at {peak} GiB with {n_res} resident stacks, {n_cached} cached patch sets")
     assert got == want
     assert int(n_res) <= 2 and int(n_cached) <= 2 and float(peak) <= limit
+
+
+def test_guard_escalates_when_the_fast_pass_breaks_its_error_premise():
+    """exact.refine_labels checks its own premise: if the cells it re-evaluates show a fast-pass error above EPS1 / 2, it warns and
+    sends EVERY cell to level 1 (with trained checkpoints the f16f8 planes could saturate silently).  Here the "fast pass"
+    is the true probability table + 2e-3 of noise and the "higher precision" returns the true table."""
+    rng = np.random.default_rng(5)
+    n, panel = 6000, "immune_full"
+    true = torch.from_numpy(_random_tables(rng, n, len(weights.VIT_SPECS[panel].classes), 1.5)).to(DEV)
+    noise = torch.from_numpy(rng.uniform(-2e-3, 2e-3, size=tuple(true.shape)).astype(np.float32)).to(DEV)
+    merge = lambda pr, want_margin=True: merge_on_device(pr, 0.3, None, want_margin=want_margin)
+    want_label, want_conf, want_counts = merge_on_device({panel: true}, 0.3, None)
+    calls = []
+
+    def forward_cells(sel, prec):
+        calls.append((int(sel.numel()), prec))
+        return {panel: true[sel]}
+
+    with pytest.warns(RuntimeWarning, match="re-evaluating all"):
+        label, conf, counts, margin, st = exact.refine_labels({panel: true + noise}, merge, forward_cells, levels=2)
+    assert st.escalated and st.reevaluated[0] == n and st.observed_error[0] > 5e-4
+    assert torch.equal(label, want_label) and torch.equal(conf, want_conf) and torch.equal(counts, want_counts)
+    assert sum(c for c, p in calls if p == "bf16x3") == n
+    # ... and with an honest fast pass (error 1e-4) nothing escalates and only the boundary cells are touched
+    calls.clear()
+    small = noise * 0.05
+    import warnings as _w
+    with _w.catch_warnings():
+        _w.simplefilter("error")
+        label, conf, counts, margin, st = exact.refine_labels({panel: true + small}, merge, forward_cells, levels=2)
+    assert not st.escalated and 0 < st.reevaluated[0] < n // 10 and st.observed_error[0] <= 1.1e-4
+    assert torch.equal(label, want_label) and torch.equal(counts, want_counts)
