@@ -572,6 +572,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t idesc = shp.fmt == kFmtF16F8 ? make_instr_desc_fmt0(2 * BM, BN) : make_instr_desc(2 * BM, BN);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
+      const int last_steps = (shp.K - (n_kb - 1) * BK + UMMA_K - 1) / UMMA_K;
       for (int pr = pair0; pr < n_pairs; pr += pair_stride, ++local) {
         const int buf = local & 1;
         const uint32_t use = (uint32_t)(local >> 1);
@@ -583,6 +584,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
+          // K steps of this K block: the last block of a K that is not a multiple of 64 (288, 144, 240, 112 ...) holds
+          // TMA zero fill beyond K - no instruction is spent on it
+#ifdef RIBCA_NO_KSKIP
+          const int nk = BK / UMMA_K;       // A/B: spend the instructions on the zero fill
+#else
+          const int nk = it == n_iter - 1 ? last_steps : BK / UMMA_K;
+#endif
           if (shp.fmt == kFmtF16F8) {
             // e4m3 pair planes (both correction terms, K doubled: 32 bytes = one K = 32 instruction per 16 elements)
             // then the fp16 planes; one accumulator, one instruction descriptor (format code 0 = E4M3 = F16)
@@ -590,14 +598,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // A/B variant: the whole K block in e4m3, then the whole K block in fp16 (profiles/r02_gemm_order.md)
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_e4m3_2sm(d_tmem, make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2), make_smem_desc_k(b_addr + w_tile + k * UMMA_K * 2),
-                            idesc, (it > 0 || k > 0) ? 1u : 0u);
+              if (k < nk)
+                umma_e4m3_2sm(d_tmem, make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2), make_smem_desc_k(b_addr + w_tile + k * UMMA_K * 2),
+                              idesc, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16_2sm(d_tmem, make_smem_desc_k(a_addr + k * UMMA_K * 2), make_smem_desc_k(b_addr + k * UMMA_K * 2), idesc, 1u);
+              if (k < nk)
+                umma_bf16_2sm(d_tmem, make_smem_desc_k(a_addr + k * UMMA_K * 2), make_smem_desc_k(b_addr + k * UMMA_K * 2), idesc, 1u);
 #else
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k >= nk) break;
               const uint64_t a_0 = make_smem_desc_k(a_addr + k * UMMA_K * 2);
               const uint64_t a_1 = make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2);
               const uint64_t w_0 = make_smem_desc_k(b_addr + k * UMMA_K * 2);
@@ -610,6 +621,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // lo.hi + hi.lo + hi.hi from the four staged tiles
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k >= nk) break;
               const uint64_t a_hi = make_smem_desc_k(a_addr + k * UMMA_K * 2);
               const uint64_t a_lo = make_smem_desc_k(a_addr + kATile + k * UMMA_K * 2);
               const uint64_t w_hi = make_smem_desc_k(b_addr + k * UMMA_K * 2);
@@ -621,8 +633,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16_2sm(d_tmem, make_smem_desc_k(a_addr + k * UMMA_K * 2), make_smem_desc_k(b_addr + k * UMMA_K * 2),
-                            idesc, (it > 0 || k > 0) ? 1u : 0u);
+              if (k < nk)
+                umma_bf16_2sm(d_tmem, make_smem_desc_k(a_addr + k * UMMA_K * 2), make_smem_desc_k(b_addr + k * UMMA_K * 2),
+                              idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm_mcast(&empty_bar[stage], (uint16_t)0x3);   // slot reusable in both CTAs once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
