@@ -67,14 +67,20 @@ def normalize_over_ranks(image, device, blur, amax, rank, nranks, phases: _Phase
         image = torch.from_numpy(image)
     c, h, w = image.shape
     out = torch.empty((c, h, w), dtype=torch.float32, device=device)
-    for k in range(rank, c, nranks):
-        plane = image[k:k + 1]
-        plane = plane.to(device, non_blocking=True) if not plane.is_cuda else plane.contiguous()
-        ops.normalize(plane, blur, amax, out=out[k:k + 1])
+    # every rank walks the planes in the same order; the owner normalises its plane right before it posts the broadcast.  The
+    # broadcasts are asynchronous (NCCL's own stream, ordered after the kernels queued so far), so the stage-1 kernels of this
+    # rank's NEXT own plane run while the finished planes travel: upload, FP64 filter and NVLink traffic overlap.
+    pending = []
+    for k in range(c):
+        if k % nranks == rank:
+            plane = image[k:k + 1]
+            plane = plane.to(device, non_blocking=True) if not plane.is_cuda else plane.contiguous()
+            ops.normalize(plane, blur, amax, out=out[k:k + 1])
+        pending.append(dist.broadcast(out[k], src=k % nranks, async_op=True))
     if phases is not None:
         phases.mark("1_upload_normalize_own_channels")
-    for k in range(c):
-        dist.broadcast(out[k], src=k % nranks)
+    for work in pending:
+        work.wait()                       # stream-level wait: the consumer kernels queue behind the last plane
     if phases is not None:
         phases.mark("1b_plane_broadcasts")
     return out
