@@ -196,13 +196,14 @@ def reference_arm(args):
     val = n / t
     what = "immune_full panel / vit_l" if args.workload == "c2" else "immune_base panel, CD11c imputed by the MAE, vit_s"
     sample = f"{edge}x{edge} crop of the {n_markers}-marker scene, {cells} cells per step, oracle (numpy/scipy/torch fp32) preprocess+predict"
-    print(json.dumps({
+    line = json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * t / max(len(rates), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload.upper()} sample: synthetic {n_markers}-marker image, {what}, {sample}"},
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(line, file=_JSON_OUT(), flush=True)
 
 
 def decision_report(ref_probs, got_probs, lab_ref, lab_got, margin_ref):
@@ -222,6 +223,11 @@ def decision_report(ref_probs, got_probs, lab_ref, lab_got, margin_ref):
             "cells_within_1e-3_of_a_decision_boundary": int((m < 1e-3).sum()), "cells_within_1e-4_of_a_decision_boundary": int((m < 1e-4).sum()),
             "cells_labelled_others_by_threshold": int((lab_ref == 17).sum().item()),
             "top2_gap_histogram": {"bin_edges": edges[:-1] + [1.0], "cells": hist}}
+
+
+def _JSON_OUT():
+    """The process's real stdout (see the bottom of the file): the one JSON line goes there."""
+    return globals().get("_json_out", sys.__stdout__)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -504,7 +510,7 @@ def main():
             "label_histogram": {ALL_TYPES[k]: int(v) for k, v in enumerate(hist) if v},
             "strong": strong, "batch": batch,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=_JSON_OUT(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -656,4 +662,8 @@ def batch_record(args, dev, world, rank, eng_full, barrier, max_over_ranks):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON record: everything the legs print on the way (the reference-shaped Annotator announces
+    # its panels with print(), like the reference) goes to stderr
+    _json_out = sys.stdout
+    sys.stdout = sys.stderr
     main()
