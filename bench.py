@@ -504,6 +504,7 @@ def main():
                     "d2h_bytes_per_step": int(n_cells * 5 + 18 * 8)},
             "e2e_annotator": e2e_annotator,
             "gpu_launches": int(launches),
+            "build": {k: _lib.build_info().get(k) for k in ("built_at_utc", "host", "nvcc", "sources_match", "gpu_visible_at_build")},
             "clocks": clocks, "roofline": roofline, "stages": stages, "reevaluation": refine,
             "cpu_baseline": cpu_baseline, "parity_sample": agreement,
             "parity_population": None if ref_gpu is None else ref_gpu["full_population_parity"],

@@ -72,7 +72,51 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: " + " ".join(link) + "\n" + r.stdout)
+    _write_build_info(nvcc)
     return LIB_PATH
+
+
+BUILD_INFO_PATH = LIB_PATH + ".build.json"        # travels with the .so (git-ignored, not gpurun-ignored)
+
+
+def _sources_digest() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for path in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(INCLUDE, "*.h"))):
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
+    return h.hexdigest()
+
+
+def _write_build_info(nvcc: str) -> None:
+    import json
+    import platform
+    import time
+    ver = subprocess.run([nvcc, "--version"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout.strip().splitlines()
+    info = {"built_at_utc": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "host": platform.node(), "nvcc": ver[-1] if ver else "",
+            "flags": NVCC_FLAGS[:-1], "sources_sha256": _sources_digest(), "gpu_visible_at_build": _gpu_visible()}
+    with open(BUILD_INFO_PATH, "w") as f:
+        json.dump(info, f, indent=1)
+
+
+def _gpu_visible() -> bool:
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
+def build_info() -> dict:
+    """Where and from what the loaded library was built (`build()` writes it next to the .so): `sources_match` tells whether
+    the sources in the tree are the ones it was compiled from."""
+    import json
+    try:
+        info = json.load(open(BUILD_INFO_PATH))
+    except Exception:
+        return {"built_at_utc": None, "sources_match": None}
+    info["sources_match"] = info.get("sources_sha256") == _sources_digest()
+    return info
 
 
 class LnFold(C.Structure):

@@ -31,6 +31,8 @@ def test_library_builds_and_exports_every_header_symbol():
     nm = subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (ribca_[a-z0-9_]+)", nm))
     assert declared <= exported
+    info = _lib.build_info()                 # the build record that travels with the .so: which sources, when, where
+    assert info["sources_match"] and info["nvcc"] and info["built_at_utc"]
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions():
