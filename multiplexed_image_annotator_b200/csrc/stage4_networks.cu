@@ -709,7 +709,8 @@ int ribca_vit_forward(const ribca_vit_desc* desc, const float* wf32, const void*
     return vit_forward_f32(desc, wf32, static_cast<const float*>(wsplit_), patches, n_cells, probs, logits, b.x,
                            reinterpret_cast<float*>(b.a), b.qkv, reinterpret_cast<float*>(b.h), st);
   }
-  RIBCA_REQUIRE(!desc->ln_folded || desc->dim % 32 == 0 || desc->dim % 16 == 0, "ribca_vit_forward: dim %d", desc->dim);
+  RIBCA_REQUIRE(desc->ln_folded >= 0 && desc->ln_folded <= 3 && (!desc->ln_folded || desc->dim % 16 == 0),
+                "ribca_vit_forward: LayerNorm fold mask %d needs dim %% 16 == 0 (dim %d)", desc->ln_folded, desc->dim);
   RIBCA_REQUIRE(desc->plane_format == fmt_of(precision), "ribca_vit_forward: weights are packed in plane format %d but precision %d needs %d",
                 desc->plane_format, precision, fmt_of(precision));
   const int n0 = interleave_enabled() ? interleave_split(n_cells) : 0;
