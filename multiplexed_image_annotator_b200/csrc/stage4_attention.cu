@@ -346,7 +346,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// head_dim 24 / 32 / 48 (every classifier but nerve_cell; 48 = vit_l, the headline): THREE item groups per CTA.
+// head_dim 12 / 24 / 32 / 48 (every classifier; 48 = vit_l, the headline): THREE item groups per CTA.
 // The kernel above is bound by the serial chain of one (cell, head) item per group (TMA -> S MMA -> softmax -> PV MMA ->
 // output, ~5 us) with only two items in flight per SM: DRAM at 56 % and the tensor pipe at 18 % (profiles/r01h_summary.md).
 // A third item needs shared memory: the 128-byte-wide Q / K / V boxes hold 96 (or 64) bytes of head each.  Here Q and K are
@@ -362,9 +362,11 @@ constexpr int kA3TP = 112;
 constexpr int kA3T64 = kA3TP * 64;                   // 32-column tile of one plane
 constexpr int kA3T32 = kA3TP * 32;                   // 16-column tile
 constexpr int kA3V = kA3TP * 128;                    // V tile of one plane
-__host__ __device__ constexpr int a3_slot_bytes(int hdp) { return 4 * kA3T64 + 2 * kA3V + (hdp == 48 ? 4 * kA3T32 : 0); }
+__host__ __device__ constexpr int a3_slot_bytes(int hdp) {
+  return (hdp >= 32 ? 4 * kA3T64 : 0) + 2 * kA3V + ((hdp == 48 || hdp == 16) ? 4 * kA3T32 : 0);
+}
 __host__ __device__ constexpr int a3_smem_bytes(int hdp) { return 3 * a3_slot_bytes(hdp) + 1024 + 256; }
-static_assert(a3_slot_bytes(48) % 1024 == 0 && a3_slot_bytes(32) % 1024 == 0 && kA3T64 % 512 == 0 && kA3T32 % 256 == 0,
+static_assert(a3_slot_bytes(48) % 1024 == 0 && a3_slot_bytes(32) % 1024 == 0 && a3_slot_bytes(16) % 1024 == 0 && kA3T64 % 512 == 0 && kA3T32 % 256 == 0,
               "tile alignment of the swizzle modes");
 
 // K-major, 32-byte swizzle (16 bf16 per row): 8-row groups are 256 B apart, layout type 6 (SWIZZLE_32B)
@@ -382,10 +384,13 @@ __device__ __forceinline__ void group128_sync(int grp) { asm volatile("bar.sync 
 template <int HDP, int FMT>
 __global__ void __launch_bounds__(kAtt3Threads, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_constant__ CUtensorMap tmap_32,
-                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
-  static_assert(HDP == 32 || HDP == 48, "Q / K pieces: 32 columns (+ 16 for head_dim 48)");
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p,
+                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  static_assert(HDP == 16 || HDP == 32 || HDP == 48, "Q / K pieces: 32 columns (HDP >= 32) and / or 16 columns (HDP 16, 48)");
   constexpr int TP = kA3TP;
-  constexpr bool kPiece32 = HDP == 48;
+  constexpr bool kPiece64 = HDP >= 32;
+  constexpr bool kPiece32 = HDP == 48 || HDP == 16;
+  constexpr int kCol32 = kPiece64 ? 32 : 0;                  // first column of the 16-column piece inside the head
   constexpr int kSlot = a3_slot_bytes(HDP);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -401,7 +406,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
   uint64_t* bar_s = bar_qk + 2;              // S done  -> softmax, Q / K reload
   uint64_t* bar_o = bar_qk + 3;              // PV done -> output
   if (tid == 0) {
-    prefetch_tmap(&tmap_64);
+    if (kPiece64) prefetch_tmap(&tmap_64);
     if (kPiece32) prefetch_tmap(&tmap_32);
     prefetch_tmap(&tmap_v);
     prefetch_tmap(&tmap_out);
@@ -418,13 +423,15 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
   const uint32_t tmem_o = tmem_sp + 112;                   // O (fp32, HDP cols)
 
   uint8_t* slot = smem + grp * kSlot;
+  constexpr int k64Bytes = kPiece64 ? 4 * kA3T64 : 0;
   uint8_t* q64[2] = {slot, slot + kA3T64};
   uint8_t* k64[2] = {slot + 2 * kA3T64, slot + 3 * kA3T64};
-  uint8_t* v_s[2] = {slot + 4 * kA3T64, slot + 4 * kA3T64 + kA3V};
-  uint8_t* t32 = slot + 4 * kA3T64 + 2 * kA3V;
+  uint8_t* v_s[2] = {slot + k64Bytes, slot + k64Bytes + kA3V};
+  uint8_t* t32 = slot + k64Bytes + 2 * kA3V;
   uint8_t* q32[2] = {t32, t32 + kA3T32};
   uint8_t* k32[2] = {t32 + 2 * kA3T32, t32 + 3 * kA3T32};
   uint8_t* o_s = v_s[0];                     // [2 planes][tokens rows][hd] bf16, dense: the TMA store's source, in the dead V tiles
+  const bool tma_out = (p.hd % 8) == 0;      // rows of hd * 2 bytes must be multiples of 16 B for the bulk store (not head_dim 12)
 
   const uint32_t idesc_s = make_instr_desc(128, TP, false);
   const uint32_t idesc_o = make_instr_desc(128, HDP, true);
@@ -435,13 +442,15 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
   auto load_qk = [&](int item) {
     const int cell = item / p.heads, head = item - cell * p.heads;
     const int row0 = cell * p.tokens;
-    mbar_expect_tx(bar_qk, 4u * kA3T64 + (kPiece32 ? 4u * kA3T32 : 0u));
+    mbar_expect_tx(bar_qk, (kPiece64 ? 4u * kA3T64 : 0u) + (kPiece32 ? 4u * kA3T32 : 0u));
     for (int pl = 0; pl < 2; ++pl) {
-      tma_load_3d(q64[pl], &tmap_64, bar_qk, head * HDP, row0, pl);
-      tma_load_3d(k64[pl], &tmap_64, bar_qk, (p.heads + head) * HDP, row0, pl);
+      if (kPiece64) {
+        tma_load_3d(q64[pl], &tmap_64, bar_qk, head * HDP, row0, pl);
+        tma_load_3d(k64[pl], &tmap_64, bar_qk, (p.heads + head) * HDP, row0, pl);
+      }
       if (kPiece32) {
-        tma_load_3d(q32[pl], &tmap_32, bar_qk, head * HDP + 32, row0, pl);
-        tma_load_3d(k32[pl], &tmap_32, bar_qk, (p.heads + head) * HDP + 32, row0, pl);
+        tma_load_3d(q32[pl], &tmap_32, bar_qk, head * HDP + kCol32, row0, pl);
+        tma_load_3d(k32[pl], &tmap_32, bar_qk, (p.heads + head) * HDP + kCol32, row0, pl);
       }
     }
   };
@@ -464,15 +473,18 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
       uint32_t acc = 0;
 #pragma unroll
       for (int ps = 0; ps < 3; ++ps) {
-        const uint32_t qa = smem_u32(q64[pa[ps]]), kb = smem_u32(k64[pb[ps]]);
-        umma_bf16(tmem_sp, make_smem_desc_sw64(qa), make_smem_desc_sw64(kb), idesc_s, acc);
-        umma_bf16(tmem_sp, make_smem_desc_sw64(qa + 32), make_smem_desc_sw64(kb + 32), idesc_s, 1u);
+        if (kPiece64) {
+          const uint32_t qa = smem_u32(q64[pa[ps]]), kb = smem_u32(k64[pb[ps]]);
+          umma_bf16(tmem_sp, make_smem_desc_sw64(qa), make_smem_desc_sw64(kb), idesc_s, acc);
+          umma_bf16(tmem_sp, make_smem_desc_sw64(qa + 32), make_smem_desc_sw64(kb + 32), idesc_s, 1u);
+          acc = 1;
+        }
         if (kPiece32)
-          umma_bf16(tmem_sp, make_smem_desc_sw32(smem_u32(q32[pa[ps]])), make_smem_desc_sw32(smem_u32(k32[pb[ps]])), idesc_s, 1u);
+          umma_bf16(tmem_sp, make_smem_desc_sw32(smem_u32(q32[pa[ps]])), make_smem_desc_sw32(smem_u32(k32[pb[ps]])), idesc_s, acc);
         acc = 1;
       }
       umma_commit(bar_s);
-      if (k > 0) {
+      if (k > 0 && tma_out) {
         // the previous item's output store has read the V tiles (its staging): only now may this item's V land there
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         load_v(item);
@@ -541,29 +553,49 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
 #pragma unroll
       for (int c = 0; c < HDP / 16; ++c) tmem_ld16_nowait(tmem_o + lane_addr + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
       tmem_ld_wait();
-      if (row < p.tokens) {
-        const int row_b = p.hd * 2;
-        uint8_t* dh = o_s + row * row_b;
-        uint8_t* dl = o_s + p.tokens * row_b + row * row_b;
+      if (tma_out) {
+        if (row < p.tokens) {
+          const int row_b = p.hd * 2;
+          uint8_t* dh = o_s + row * row_b;
+          uint8_t* dl = o_s + p.tokens * row_b + row * row_b;
 #pragma unroll
-        for (int ch = 0; ch < HDP / 8; ++ch) {
-          if (ch * 8 < p.hd) {
-            uint32_t h[4], l[4];
+          for (int ch = 0; ch < HDP / 8; ++ch) {
+            if (ch * 8 < p.hd) {
+              uint32_t h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, FMT, h[e], l[e]);
-            *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+              for (int e = 0; e < 4; ++e) split_pair(o[ch * 8 + 2 * e] * inv, o[ch * 8 + 2 * e + 1] * inv, FMT, h[e], l[e]);
+              *reinterpret_cast<uint4*>(dh + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(dl + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
           }
         }
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      group128_sync(grp);                    // also: every thread's TMEM reads of O / P are done before the next item's MMAs
-      if (leader) {
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                     ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * p.hd), "r"(cell * p.tokens), "r"(0)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        group128_sync(grp);                    // also: every thread's TMEM reads of O / P are done before the next item's MMAs
+        if (leader) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(o_s)), "r"(head * p.hd), "r"(cell * p.tokens), "r"(0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        // head_dim 12: 24-byte rows are no TMA box; 8-byte stores straight from the registers, V is free at once
+        if (leader && k + 1 < my_items) load_v(item + stride);
+        if (row < p.tokens) {
+          const long long ob = ((long long)(cell * p.tokens + row)) * p.D + head * p.hd;
+#pragma unroll
+          for (int q4 = 0; q4 < HDP / 4; ++q4) {
+            if (q4 * 4 < p.hd) {
+              uint32_t h[2], l[2];
+              split_pair(o[q4 * 4] * inv, o[q4 * 4 + 1] * inv, FMT, h[0], l[0]);
+              split_pair(o[q4 * 4 + 2] * inv, o[q4 * 4 + 3] * inv, FMT, h[1], l[1]);
+              *reinterpret_cast<uint2*>(out_hi + ob + q4 * 4) = make_uint2(h[0], h[1]);
+              *reinterpret_cast<uint2*>(out_lo + ob + q4 * 4) = make_uint2(l[0], l[1]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        group128_sync(grp);
       }
     }
   }
@@ -580,13 +612,13 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_64, const __grid_c
 
 template <int HDP, int FMT>
 static int launch_tc3(const CUtensorMap& m64, const CUtensorMap& m32, const CUtensorMap& mv, const CUtensorMap& mo, const AttnParams& p,
-                      cudaStream_t st) {
+                      bf16* hi, bf16* lo, cudaStream_t st) {
   constexpr int kSmem = a3_smem_bytes(HDP);
   RIBCA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc3_kernel<HDP, FMT>), kSmem, "cudaFuncSetAttribute(attention_tc3_kernel)"));
   const int grid = std::min((p.cells * p.heads + 2) / 3, num_sms());
   const bool prof = profiling();
   if (prof) prof_begin_span(RIBCA_PROF_ATTENTION, 4.0 * (double)p.cells * p.heads * (double)p.tokens * p.tokens * p.hd, st);
-  attention_tc3_kernel<HDP, FMT><<<grid, kAtt3Threads, kSmem, st>>>(m64, m32, mv, mo, p);
+  attention_tc3_kernel<HDP, FMT><<<grid, kAtt3Threads, kSmem, st>>>(m64, m32, mv, mo, p, hi, lo);
   if (prof) prof_end_span(st);
   RIBCA_LAUNCH_CHECK("attention_tc3_kernel");
   return RIBCA_OK;
@@ -635,7 +667,7 @@ static int launch_tc_hdp(const CUtensorMap& mq, const CUtensorMap& mkv, const CU
   }
 }
 
-// RIBCA_ATTN3=0 keeps the two-group kernel for head_dim 24 / 32 / 48 (A/B)
+// RIBCA_ATTN3=0 keeps the two-group kernel for head_dim 12 / 24 / 32 / 48 (A/B)
 static bool three_groups_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RIBCA_ATTN3"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -673,13 +705,15 @@ int attention_tc_launch(const void* qkv_split, long long qkv_plane, int cells, i
   }
   bf16* hi = static_cast<bf16*>(out_split);
   bf16* lo = hi + out_plane;
-  if ((p.hdp == 48 || p.hdp == 32) && hd % 8 == 0 && tokens > 96 && three_groups_enabled()) {
-    // head_dim 24 / 32 / 48: three item groups per CTA, unpadded Q / K tiles (attention_tc3_kernel)
+  if (p.hdp <= 48 && (hd % 8 == 0 || p.hdp == 16) && tokens > 96 && three_groups_enabled()) {
+    // head_dim 12 / 24 / 32 / 48: three item groups per CTA, unpadded Q / K tiles (attention_tc3_kernel)
     CUtensorMap m64, m32;
     RIBCA_TRY(make_qkv_map(&m64, qkv_split, qkv_plane, M, width, TP, 32));
     RIBCA_TRY(make_qkv_map(&m32, qkv_split, qkv_plane, M, width, TP, 16));
-    if (p.hdp == 48) return out_fmt == kFmtF16F8 ? launch_tc3<48, kFmtF16F8>(m64, m32, mkv, mo, p, st) : launch_tc3<48, kFmtBf16>(m64, m32, mkv, mo, p, st);
-    return out_fmt == kFmtF16F8 ? launch_tc3<32, kFmtF16F8>(m64, m32, mkv, mo, p, st) : launch_tc3<32, kFmtBf16>(m64, m32, mkv, mo, p, st);
+    const bool f8 = out_fmt == kFmtF16F8;
+    if (p.hdp == 48) return f8 ? launch_tc3<48, kFmtF16F8>(m64, m32, mkv, mo, p, hi, lo, st) : launch_tc3<48, kFmtBf16>(m64, m32, mkv, mo, p, hi, lo, st);
+    if (p.hdp == 32) return f8 ? launch_tc3<32, kFmtF16F8>(m64, m32, mkv, mo, p, hi, lo, st) : launch_tc3<32, kFmtBf16>(m64, m32, mkv, mo, p, hi, lo, st);
+    return f8 ? launch_tc3<16, kFmtF16F8>(m64, m32, mkv, mo, p, hi, lo, st) : launch_tc3<16, kFmtBf16>(m64, m32, mkv, mo, p, hi, lo, st);
   }
   return out_fmt == kFmtF16F8 ? launch_tc_hdp<TP, kFmtF16F8>(mq, mkv, mo, p, hi, lo, st)
                               : launch_tc_hdp<TP, kFmtBf16>(mq, mkv, mo, p, hi, lo, st);
