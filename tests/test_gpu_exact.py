@@ -299,3 +299,19 @@ def test_guard_escalates_when_the_fast_pass_breaks_its_error_premise():
         label, conf, counts, margin, st = exact.refine_labels({panel: true + small}, merge, forward_cells, levels=2)
     assert not st.escalated and 0 < st.reevaluated[0] < n // 10 and st.observed_error[0] <= 1.1e-4
     assert torch.equal(label, want_label) and torch.equal(counts, want_counts)
+
+
+def test_hot_path_on_an_image_without_cells_and_with_one_cell():
+    """Edge cases of the whole path: an empty mask gives empty labels and zero counts (the reference would write an empty CSV),
+    a single cell goes through every stage (chunk of 1, no re-evaluation batch of size 0 issues)."""
+    panel = "nerve_cell"
+    eng = engine.VitEngine(panel, weights.random_vit_state(panel, seed=2), DEV)
+    hp = HotPath({panel: [0, 1, 2]}, {panel: eng}, device=DEV)
+    img = (np.random.default_rng(0).random((3, 96, 96)) * 4000).astype(np.uint16)
+    mask = np.zeros((96, 96), np.int32)
+    res = hp.run(img, mask)
+    assert res.n_cells == 0 and res.label.numel() == 0 and res.confidence.numel() == 0 and int(res.counts.sum()) == 0
+    mask[40:52, 30:44] = 7                                    # one cell with label 7
+    res = hp.run(img, mask)
+    assert res.n_cells == 1 and res.label.numel() == 1 and int(res.counts.sum()) == 1
+    assert ALL_TYPES[int(res.label[0])] in tuple(weights.VIT_SPECS[panel].classes) + (OTHERS,)
