@@ -314,4 +314,4 @@ def test_hot_path_on_an_image_without_cells_and_with_one_cell():
     mask[40:52, 30:44] = 7                                    # one cell with label 7
     res = hp.run(img, mask)
     assert res.n_cells == 1 and res.label.numel() == 1 and int(res.counts.sum()) == 1
-    assert ALL_TYPES[int(res.label[0])] in tuple(weights.VIT_SPECS[panel].classes) + (OTHERS,)
+    assert ALL_TYPES[int(res.label[0])] in tuple(weights.VIT_SPECS[panel].classes) + (ALL_TYPES[OTHERS],)
