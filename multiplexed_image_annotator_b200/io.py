@@ -223,10 +223,12 @@ def iter_tiff_planes(path, pin: bool = True):
                 yield k * p0.samples + j, out
 
 
-def iter_npy_planes(path, pin: bool = True):
+def iter_npy_planes(path, pin: bool = True, threads: int = 4):
     """The .npy counterpart of iter_tiff_planes: a C-ordered (C, H, W) / (H, W) array of a native numeric dtype is read plane by
-    plane with `readinto` into ONE (pinned) buffer; yields (k, stack) after plane k is complete.  Anything else (Fortran order,
-    object arrays, other ranks) raises ValueError and the caller falls back to np.load."""
+    plane (positional reads straight into ONE (pinned) buffer, up to `threads` planes in flight: the page-cache copy of one
+    thread is ~3 GB/s); yields (k, stack) in order, after plane k is complete.  Anything else (Fortran order, object arrays,
+    other ranks) raises ValueError and the caller falls back to np.load."""
+    from concurrent.futures import ThreadPoolExecutor
     with open(path, "rb") as f:
         version = np.lib.format.read_magic(f)
         shape, fortran, dtype = (np.lib.format.read_array_header_1_0 if version == (1, 0) else np.lib.format.read_array_header_2_0)(f)
@@ -235,15 +237,26 @@ def iter_npy_planes(path, pin: bool = True):
             raise ValueError(f"{path}: not a C-ordered uint8 / uint16 / int32 / float32 image stack")
         c, h, w = shape if len(shape) == 3 else (1,) + tuple(shape)
         out, _owner = _alloc((c, h, w), dtype, pin)
-        for k in range(c):
+        base, plane_bytes, fd = f.tell(), h * w * np.dtype(dtype).itemsize, f.fileno()
+
+        def read_plane(k):
             dst = memoryview(out[k]).cast("B")
             got = 0
-            while got < len(dst):
-                n = f.readinto(dst[got:])
+            while got < plane_bytes:
+                n = os.preadv(fd, [dst[got:]], base + k * plane_bytes + got)
                 if not n:
                     raise ValueError(f"{path}: truncated file")
                 got += n
-            yield k, out
+            return k
+
+        with ThreadPoolExecutor(max_workers=max(1, min(threads, c))) as pool:
+            ahead = max(1, min(threads, c))
+            futs = [pool.submit(read_plane, k) for k in range(min(ahead, c))]
+            for k in range(c):
+                futs[k].result()
+                if k + ahead < c:
+                    futs.append(pool.submit(read_plane, k + ahead))
+                yield k, out
 
 
 def is_npy(path) -> bool:
